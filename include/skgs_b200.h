@@ -1,0 +1,220 @@
+/*
+ * skgs_b200.h - C ABI of the B200-native SK_GS hot path (libskgs_b200.so).
+ *
+ * Plain pointers and sizes only (no torch types).  All pointers are DEVICE pointers unless the name ends in `_host`.
+ * Every entry point enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises the host,
+ * returns 0 on success or a negative skgs_status and records a message retrievable with skgs_last_error().
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   skgs_raster_forward        <- my_ext/_C/src/nerf/gaussian_rasterizer_forward.cu:260-315 `rasterize_gaussians`
+ *                                 (RasterizeGaussiansCUDA -> Rasterizer::forward :157-250) and the un-vendored
+ *                                 diff_gaussian_rasterization `_C.rasterize_gaussians` behind
+ *                                 networks/renderer/gaussian_render_origin.py:36-52
+ *   skgs_raster_backward       <- my_ext/_C/src/nerf/gaussian_rasterizer_backwrad.cu:200-261
+ *                                 `rasterize_gaussians_backward` (Rasterizer::backward :148-198)
+ *   skgs_raster_layout         <- GeometryState/ImageState/BinningState::fromChunk + required<T>()
+ *                                 my_ext/_C/src/nerf/gaussian_rasterizer_imp.cu:39-73, include/gaussian_render.h:111-158
+ *   skgs_fk_lbs_forward/backward <- networks/sk_gs.py:1069-1150 (`kinematic` post-MLP + `skeleton_warp_SE3` :193-206 +
+ *                                 `calc_LBS_weight` :751-774 + LBS blend :1147-1149); there is no native boundary in the
+ *                                 reference (lietorch + pytorch3d ops), this is the new one
+ *   skgs_assemble_forward/backward <- output assembly networks/sk_gs.py:1162-1163,1192,1202-1203 with the activations
+ *                                 of networks/gaussian_splatting.py:155-160
+ */
+#ifndef SKGS_B200_H_
+#define SKGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SKGS_API __attribute__((visibility("default")))
+#else
+#define SKGS_API
+#endif
+
+typedef enum skgs_status {
+  SKGS_OK = 0,
+  SKGS_ERR_INVALID_ARG = -1,
+  SKGS_ERR_CUDA = -2,
+  SKGS_ERR_UNSUPPORTED = -3,
+  SKGS_ERR_WORKSPACE = -4
+} skgs_status;
+
+/* thread-local message of the last failing call on this thread ("" if none) */
+SKGS_API const char* skgs_last_error(void);
+/* library version, increases whenever the ABI changes */
+SKGS_API int skgs_abi_version(void);
+/* compute capability this library was built for (100 = sm_100a) */
+SKGS_API int skgs_built_for_sm(void);
+/* number of kernels launched by this process through the library so far (bench.py's `gpu_launches`) */
+SKGS_API uint64_t skgs_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rasterizer
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Mirrors GaussianRasterizationSettings (networks/gaussian_splatting.py:271-284; networks/renderer/gaussian_render.py:34-48).
+ * Matrices are the torch row-major tensors viewmatrix = Tw2v.T and projmatrix = (Tv2c @ Tw2v).T (16 floats each). */
+typedef struct skgs_raster_settings {
+  int32_t image_height;
+  int32_t image_width;
+  float tanfovx;
+  float tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;        /* active degree D, 0..3 */
+  int32_t quat_wxyz;        /* 1: rotations are (w,x,y,z) (upstream boundary B1); 0: (x,y,z,w) (in-tree boundary B2) */
+  int32_t prefiltered;      /* accepted for API parity; culled points are simply skipped */
+  int32_t debug;            /* accepted for API parity */
+  const float* viewmatrix;  /* device [16] */
+  const float* projmatrix;  /* device [16] */
+  const float* campos;      /* device [3] */
+  const float* bg;          /* device [3] or NULL (= black) */
+} skgs_raster_settings;
+
+/* Byte offsets of every array inside the three caller-owned arenas (all 256-byte aligned).
+ * geom arena (per Gaussian, written by forward, read by backward):                                   */
+typedef struct skgs_raster_layout {
+  size_t geom_bytes, binning_bytes, img_bytes;
+  /* geom */
+  size_t header;         /* skgs_raster_header */
+  size_t means2D;        /* float2 [P]   pixel-space centre */
+  size_t depths;         /* float  [P]   view-space z */
+  size_t cov3D;          /* float  [P][6] */
+  size_t conic_opacity;  /* float4 [P]   (conic a, b, c, opacity) */
+  size_t rgbd;           /* float4 [P]   (r, g, b, depth) */
+  size_t clamped;        /* uint8  [P]   bit c set <=> colour channel c was clamped at 0 */
+  size_t tiles_touched;  /* uint32 [P] */
+  size_t point_offsets;  /* uint32 [P]   inclusive prefix sum of tiles_touched */
+  size_t scan_state;     /* uint64 [ceil(P/256)+1] look-back words of the fused scan */
+  size_t geom_grads;     /* float  [P][12] packed backward accumulators (see skgs_raster_backward) */
+  /* binning (capacity R_cap entries) */
+  size_t keys_unsorted;  /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */
+  size_t vals_unsorted;  /* uint32 [R_cap] */
+  size_t keys_sorted;    /* uint64 [R_cap] */
+  size_t point_list;     /* uint32 [R_cap]  Gaussian ids sorted by (tile, depth), stable */
+  size_t sort_hist;      /* uint32 [8][256] digit histograms */
+  size_t sort_status;    /* uint32 [passes][tiles_of_keys][256] look-back words + tickets */
+  /* img */
+  size_t ranges;         /* uint2  [tiles] */
+  size_t n_contrib;      /* uint32 [H*W] */
+  size_t final_T;        /* float  [H*W] */
+} skgs_raster_layout;
+
+/* Lives at geom + layout.header; written on the device, never read by the library on the host. */
+typedef struct skgs_raster_header {
+  uint32_t num_rendered;  /* R = sum tiles_touched (may exceed R_cap) */
+  uint32_t num_visible;   /* Gaussians with radius > 0 */
+  uint32_t scan_ticket;   /* internal */
+  uint32_t overflow;      /* 1 if R > R_cap: the image of this call is INVALID, re-run with a larger binning arena */
+  uint32_t sort_ticket[8]; /* internal */
+  uint32_t reserved[4];
+} skgs_raster_header;
+
+SKGS_API int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skgs_raster_layout* out);
+
+/* Forward: preprocess (+fused prefix sum) -> duplicate-with-keys (+digit histograms) -> onesweep radix sort ->
+ * tile ranges -> per-tile compositing.  Exactly one of shs / colors_precomp and one of (scales, rotations) /
+ * cov3D_precomp must be non-NULL (same rule as networks/renderer/gaussian_render.py:250-255).
+ *   means3D [P][3], shs [P][M][3], colors_precomp [P][3], opacities [P], scales [P][3], rotations [P][4], cov3D_precomp [P][6]
+ *   out_color [3][H][W], out_depth [H][W], out_alpha [H][W] (= 1 - T), radii int32 [P]
+ *   num_rendered_host: optional PINNED host uint32[4] that receives the first four header words
+ *   {R, num_visible, -, overflow} by an async copy enqueued after the scan and again after key emission.
+ * P == 0 is legal (image = background). */
+SKGS_API int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                 const float* shs, const float* colors_precomp, const float* opacities,
+                                 const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
+                                 void* binning, int64_t R_cap, void* img, float* out_color, float* out_depth,
+                                 float* out_alpha, int32_t* radii, uint32_t* num_rendered_host, void* stream);
+
+/* Forward split in two for callers that want R before sizing the binning arena:
+ *   _geometry: preprocess + scan (+ async copy of the header words to num_rendered_host)
+ *   _render  : duplicate + sort + ranges + composite, for the R_cap the binning arena was sized for.          */
+SKGS_API int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                          const float* shs, const float* colors_precomp, const float* opacities,
+                                          const float* scales, const float* rotations, const float* cov3D_precomp,
+                                          void* geom, int32_t* radii, uint32_t* num_rendered_host, void* stream);
+SKGS_API int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning,
+                                        int64_t R_cap, int64_t R_hint, void* img, const int32_t* radii,
+                                        float* out_color, float* out_depth, float* out_alpha,
+                                        uint32_t* num_rendered_host, void* stream);
+
+/* Backward.  dL_dcolor [3][H][W] is required; dL_ddepth / dL_dalpha [H][W] may be NULL.
+ * Outputs (each may be NULL when the corresponding input was absent): dL_dmeans3D [P][3], dL_dmeans2D [P][3]
+ * (screen-space gradient used by densification, z = 0), dL_dsh [P][M][3], dL_dcolors [P][3], dL_dopacity [P],
+ * dL_dscales [P][3], dL_drotations [P][4] (same quaternion layout as the input), dL_dcov3D [P][6].
+ * All outputs are fully written (zeros for culled Gaussians), no pre-zeroing needed. */
+SKGS_API int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                  const float* shs, const float* colors_precomp, const float* scales,
+                                  const float* rotations, const float* cov3D_precomp, const int32_t* radii, void* geom,
+                                  const void* binning, int64_t R_cap, const void* img, const float* dL_dcolor,
+                                  const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D,
+                                  float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
+                                  float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Skeleton forward kinematics + linear blend skinning (+ optional output assembly)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef enum skgs_lbs_mode {
+  SKGS_LBS_W = 0,               /* softmax(gather(sp_W, idx))                      networks/sk_gs.py:767-768 */
+  SKGS_LBS_KERNEL = 1,          /* exp(-d2/(2 r^2)) + 1e-7, L1-normalised          :760-766 */
+  SKGS_LBS_WEIGHTED_KERNEL = 2, /* ... * sigmoid(weight)                           :763-764 */
+  SKGS_LBS_DIST = 3             /* softmax(-d2 / temperature)                      :769-770 */
+} skgs_lbs_mode;
+
+typedef struct skgs_skeleton {
+  int32_t M;               /* joints, 1..1024 */
+  int32_t L;               /* levels of the binary-lifting table */
+  int32_t root;
+  int32_t K;               /* nearest joints per Gaussian, 1..8, <= M */
+  int32_t mode;            /* skgs_lbs_mode */
+  float temperature;       /* SKGS_LBS_DIST only */
+  const float* joints;     /* [M][3] */
+  const float* sk_r;       /* [M][4] xyzw local joint rotation (normalised inside, like lietorch) */
+  const float* sk_r_delta; /* NULL, or [M][3] axis-angle / [M][4] quaternion repose delta (networks/sk_gs.py:1087-1088) */
+  int32_t sk_r_delta_dim;  /* 3 or 4 */
+  const float* sk_d_rot;   /* [M][4] */
+  const float* sk_d_scale; /* [M][3] */
+  const float* g_tr;       /* [7] (t, q xyzw) global transform or NULL (identity) */
+  const int32_t* parents;  /* [M][L], parents[:, l] = 2^l-th ancestor, parents[root, :] = root */
+  const float* sp_W;       /* [P][M]   (mode W) */
+  const float* sp_radius;  /* [M] log-radius (kernel modes) */
+  const float* sp_weight;  /* [M] logit (weighted_kernel) */
+} skgs_skeleton;
+
+/* Forward.  xyz [P][3] (treated as constant: the reference detaches it, networks/sk_gs.py:1113).
+ * Outputs: d_xyz [P][3], d_rot [P][4], d_scale [P][3], sk_T [M][7] (t, q xyzw), weights [P][K], indices int64 [P][K]. */
+SKGS_API int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, float* d_xyz, float* d_rot,
+                                 float* d_scale, float* sk_T, float* weights, int64_t* indices, void* stream);
+
+/* Backward.  Incoming: dL_dd_xyz [P][3], dL_dd_rot [P][4], dL_dd_scale [P][3] (any may be NULL = zero), plus optional
+ * direct gradients on the auxiliary outputs dL_dsk_T [M][7], dL_dweights [P][K] (NULL = zero).
+ * Outgoing (NULL = not wanted): dL_djoints [M][3], dL_dsk_r [M][4], dL_dsk_d_rot [M][4], dL_dsk_d_scale [M][3],
+ * dL_dg_tr [7], dL_dsp_W [P][M] (dense, K non-zeros per row), dL_dsp_radius [M], dL_dsp_weight [M].
+ * workspace: device scratch of skgs_fk_lbs_workspace_bytes(M) bytes. */
+SKGS_API size_t skgs_fk_lbs_workspace_bytes(int32_t M);
+SKGS_API int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, const float* sk_T,
+                                  const float* weights, const int64_t* indices, const float* dL_dd_xyz,
+                                  const float* dL_dd_rot, const float* dL_dd_scale, const float* dL_dsk_T,
+                                  const float* dL_dweights, float* dL_djoints, float* dL_dsk_r, float* dL_dsk_d_rot,
+                                  float* dL_dsk_d_scale, float* dL_dg_tr, float* dL_dsp_W, float* dL_dsp_radius,
+                                  float* dL_dsp_weight, void* workspace, void* stream);
+
+/* Output assembly: points = _xyz + d_xyz, scales = exp(_scaling) + d_scale, rotations = normalize(_rotation + d_rot)
+ * (eps 1e-12), opacity = sigmoid(_opacity).  d_* may be NULL (static stage). */
+SKGS_API int skgs_assemble_forward(int32_t P, const float* xyz, const float* scaling, const float* rotation,
+                                   const float* opacity, const float* d_xyz, const float* d_rot, const float* d_scale,
+                                   float* points, float* scales, float* rotations, float* opacities, void* stream);
+SKGS_API int skgs_assemble_backward(int32_t P, const float* scaling, const float* rotation, const float* opacity,
+                                    const float* d_rot, const float* dL_dpoints, const float* dL_dscales,
+                                    const float* dL_drotations, const float* dL_dopacities, float* dL_dxyz,
+                                    float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_xyz,
+                                    float* dL_dd_rot, float* dL_dd_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKGS_B200_H_ */

@@ -1,0 +1,105 @@
+"""ctypes binding of libskgs_b200.so (the C ABI declared in include/skgs_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(the reference degrades to Python fallbacks on ImportError, my_ext/_C/__init__.py:100-126; this package must not).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libskgs_b200.so')
+
+c_f32p = C.c_void_p  # all device pointers travel as integers (tensor.data_ptr())
+
+
+class RasterSettings(C.Structure):
+    _fields_ = [
+        ('image_height', C.c_int32), ('image_width', C.c_int32), ('tanfovx', C.c_float), ('tanfovy', C.c_float),
+        ('scale_modifier', C.c_float), ('sh_degree', C.c_int32), ('quat_wxyz', C.c_int32),
+        ('prefiltered', C.c_int32), ('debug', C.c_int32), ('viewmatrix', C.c_void_p), ('projmatrix', C.c_void_p),
+        ('campos', C.c_void_p), ('bg', C.c_void_p),
+    ]
+
+
+_LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
+                  'rgbd', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads', 'keys_unsorted',
+                  'vals_unsorted', 'keys_sorted', 'point_list', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
+                  'final_T']
+
+
+class RasterLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in _LAYOUT_FIELDS]
+
+
+class Skeleton(C.Structure):
+    _fields_ = [
+        ('M', C.c_int32), ('L', C.c_int32), ('root', C.c_int32), ('K', C.c_int32), ('mode', C.c_int32),
+        ('temperature', C.c_float), ('joints', C.c_void_p), ('sk_r', C.c_void_p), ('sk_r_delta', C.c_void_p),
+        ('sk_r_delta_dim', C.c_int32), ('sk_d_rot', C.c_void_p), ('sk_d_scale', C.c_void_p), ('g_tr', C.c_void_p),
+        ('parents', C.c_void_p), ('sp_W', C.c_void_p), ('sp_radius', C.c_void_p), ('sp_weight', C.c_void_p),
+    ]
+
+
+LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
+
+# every symbol include/skgs_b200.h declares: (restype, argtypes)
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+_SIGNATURES = {
+    'skgs_last_error': (C.c_char_p, []),
+    'skgs_abi_version': (C.c_int, []),
+    'skgs_built_for_sm': (C.c_int, []),
+    'skgs_launch_count': (C.c_uint64, []),
+    'skgs_raster_layout_query': (C.c_int, [_i32, _i32, _i32, _i64, C.POINTER(RasterLayout)]),
+    'skgs_raster_forward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 8 + [_vp, _i64, _vp] +
+                            [_vp] * 6),
+    'skgs_raster_forward_geometry': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp] * 4),
+    'skgs_raster_forward_render': (C.c_int, [C.POINTER(RasterSettings), _i32, _vp, _vp, _i64, _i64, _vp] + [_vp] * 6),
+    'skgs_raster_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp, _vp, _i64, _vp] +
+                             [_vp] * 12),
+    'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 8),
+    'skgs_fk_lbs_workspace_bytes': (C.c_size_t, [_i32]),
+    'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 19),
+    'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),
+    'skgs_assemble_backward': (C.c_int, [_i32] + [_vp] * 16),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first. '
+                               f'sk_gs_b200 has no CPU / PyTorch fallback.')
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check_exports():
+    """Load the library and verify every declared symbol is exported (no compute call; works without a GPU)."""
+    L = lib()
+    assert L.skgs_abi_version() == 1
+    assert L.skgs_built_for_sm() == 100
+    return sorted(_SIGNATURES)
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f'{what} failed ({rc}): {lib().skgs_last_error().decode()}')
+
+
+def launch_count() -> int:
+    return int(lib().skgs_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,237 @@
+// api.cu - C ABI glue of libskgs_b200.so: error reporting, arena layout, rasterizer entry points.
+// See include/skgs_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace skgs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sort_passes(int gx, int gy);
+
+constexpr int OS_TILE_KEYS = 4096;  // must match OS_TILE in raster_fwd.cu
+constexpr size_t ARENA_ALIGN = 256;
+
+static int fill_params(const skgs_raster_settings* s, int P, int M, RasterParams& rp) {
+  SKGS_CHECK_ARG(s != nullptr, "settings is NULL");
+  SKGS_CHECK_ARG(s->image_width > 0 && s->image_height > 0, "image size must be positive (got %d x %d)",
+                 s->image_width, s->image_height);
+  SKGS_CHECK_ARG(s->viewmatrix && s->projmatrix && s->campos, "viewmatrix / projmatrix / campos must be device pointers");
+  SKGS_CHECK_ARG(s->sh_degree >= 0 && s->sh_degree <= 3, "sh_degree %d not in 0..3", s->sh_degree);
+  SKGS_CHECK_ARG(P >= 0, "P < 0");
+  rp.P = P;
+  rp.M = M;
+  rp.D = s->sh_degree;
+  rp.W = s->image_width;
+  rp.H = s->image_height;
+  rp.gx = (rp.W + TILE - 1) / TILE;
+  rp.gy = (rp.H + TILE - 1) / TILE;
+  rp.tanfovx = s->tanfovx;
+  rp.tanfovy = s->tanfovy;
+  rp.fy = rp.H / (2.0f * s->tanfovy);  // gaussian_rasterizer_forward.cu:163-164
+  rp.fx = rp.W / (2.0f * s->tanfovx);
+  rp.mod = s->scale_modifier;
+  rp.quat_wxyz = s->quat_wxyz;
+  rp.view = s->viewmatrix;
+  rp.proj = s->projmatrix;
+  rp.campos = s->campos;
+  rp.bg = s->bg;
+  return SKGS_OK;
+}
+
+static int check_inputs(const skgs_raster_settings* s, int P, int M, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        const float* rotations, const float* cov3D_precomp) {
+  if (P == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(means3D != nullptr, "means3D is NULL");
+  SKGS_CHECK_ARG(opacities != nullptr, "opacities is NULL");
+  // same rule as networks/renderer/gaussian_render.py:250-255
+  SKGS_CHECK_ARG((shs == nullptr) != (colors_precomp == nullptr),
+                 "Please provide excatly one of either SHs or precomputed colors!");
+  SKGS_CHECK_ARG(((scales == nullptr && rotations == nullptr) && cov3D_precomp != nullptr) ||
+                     ((scales != nullptr && rotations != nullptr) && cov3D_precomp == nullptr),
+                 "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+  if (shs) {
+    SKGS_CHECK_ARG(M >= (s->sh_degree + 1) * (s->sh_degree + 1) && M <= 16,
+                   "sh has %d coefficients, degree %d needs %d (max 16)", M, s->sh_degree,
+                   (s->sh_degree + 1) * (s->sh_degree + 1));
+  }
+  return SKGS_OK;
+}
+
+}  // namespace skgs
+
+using namespace skgs;
+
+extern "C" {
+
+const char* skgs_last_error(void) { return g_err; }
+int skgs_abi_version(void) { return 1; }
+int skgs_built_for_sm(void) { return 100; }
+uint64_t skgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skgs_raster_layout* out) {
+  SKGS_CHECK_ARG(out != nullptr, "layout is NULL");
+  SKGS_CHECK_ARG(P >= 0 && W > 0 && H > 0 && R_cap >= 0, "bad sizes P=%d W=%d H=%d R_cap=%lld", P, W, H,
+                 (long long)R_cap);
+  SKGS_CHECK_ARG(R_cap < (1ll << 27), "R_cap=%lld exceeds the 2^27 entries of the sort's look-back word",
+                 (long long)R_cap);
+  memset(out, 0, sizeof(*out));
+  const size_t Pz = (size_t)P;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, ARENA_ALIGN);
+    return at;
+  };
+  // ---- geom (header + scan_state first: they are reset by one memset per forward)
+  out->header = take(sizeof(skgs_raster_header));
+  out->scan_state = take(((Pz + 255) / 256 + 1) * sizeof(uint64_t));
+  out->means2D = take(Pz * 8);
+  out->depths = take(Pz * 4);
+  out->cov3D = take(Pz * 24);
+  out->conic_opacity = take(Pz * 16);
+  out->rgbd = take(Pz * 16);
+  out->clamped = take(Pz);
+  out->tiles_touched = take(Pz * 4);
+  out->point_offsets = take(Pz * 4);
+  out->geom_grads = take(Pz * 48);
+  out->geom_bytes = o;
+  // ---- binning
+  o = 0;
+  const size_t Rz = (size_t)R_cap;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int passes = sort_passes(gx, gy);
+  const size_t kA = take(Rz * 8), vA = take(Rz * 4), kB = take(Rz * 8), vB = take(Rz * 4);
+  // keys are emitted into A; pass p writes to B, A, B, ...  The final result is in B for an odd number of passes and
+  // back in A for an even number: report the physical location of the FINAL lists as keys_sorted / point_list.
+  if (passes % 2 == 1) {
+    out->keys_unsorted = kA; out->vals_unsorted = vA; out->keys_sorted = kB; out->point_list = vB;
+  } else {
+    out->keys_unsorted = kA; out->vals_unsorted = vA; out->keys_sorted = kA; out->point_list = vA;
+  }
+  (void)kB;
+  (void)vB;
+  out->sort_hist = take(8 * 256 * sizeof(uint32_t));
+  out->sort_status = take(((Rz + OS_TILE_KEYS - 1) / OS_TILE_KEYS + 1) * 256 * sizeof(uint32_t));
+  out->binning_bytes = o;
+  // ---- img
+  o = 0;
+  out->ranges = take((size_t)gx * gy * 8);
+  out->n_contrib = take((size_t)W * H * 4);
+  out->final_T = take((size_t)W * H * 4);
+  out->img_bytes = o;
+  return SKGS_OK;
+}
+
+// physical A/B buffers regardless of pass parity (internal)
+static void physical_buffers(const skgs_raster_layout& lay, int64_t R_cap, skgs_raster_layout& phys) {
+  phys = lay;
+  const size_t Rz = (size_t)R_cap;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, ARENA_ALIGN);
+    return at;
+  };
+  phys.keys_unsorted = take(Rz * 8);
+  phys.vals_unsorted = take(Rz * 4);
+  phys.keys_sorted = take(Rz * 8);
+  phys.point_list = take(Rz * 4);
+}
+
+int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                 const float* shs, const float* colors_precomp, const float* opacities,
+                                 const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
+                                 int32_t* radii, uint32_t* num_rendered_host, void* stream) {
+  RasterParams rp;
+  int rc = fill_params(s, P, M, rp);
+  if (rc) return rc;
+  rc = check_inputs(s, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(geom != nullptr && (P == 0 || radii != nullptr), "geom arena / radii is NULL");
+  skgs_raster_layout lay;
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, 0, &lay);
+  if (rc) return rc;
+  return launch_preprocess_scan(rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                (char*)geom, lay, radii, num_rendered_host, (cudaStream_t)stream);
+}
+
+int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning, int64_t R_cap,
+                               int64_t R_hint, void* img, const int32_t* radii, float* out_color, float* out_depth,
+                               float* out_alpha, uint32_t* num_rendered_host, void* stream) {
+  RasterParams rp;
+  int rc = fill_params(s, P, 0, rp);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(geom && img && out_color && out_depth && out_alpha, "NULL arena / output");
+  SKGS_CHECK_ARG(R_cap == 0 || binning != nullptr, "binning arena is NULL");
+  skgs_raster_layout lay, phys;
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, R_cap, &lay);
+  if (rc) return rc;
+  physical_buffers(lay, R_cap, phys);
+  cudaStream_t st = (cudaStream_t)stream;
+  // reset the overflow flag and the sort tickets (the render stage may be re-run on the same geometry)
+  auto* hdr = reinterpret_cast<skgs_raster_header*>((char*)geom + lay.header);
+  SKGS_CUDA(cudaMemsetAsync(&hdr->overflow, 0, sizeof(uint32_t) * 9, st));
+  rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, phys, radii, R_cap, R_hint, num_rendered_host, st);
+  if (rc) return rc;
+  if (s->debug & 2) return SKGS_OK;  // test hook: stop after binning
+  return launch_composite_fwd(rp, (char*)geom, (char*)binning, (char*)img, lay, out_color, out_depth, out_alpha, st);
+}
+
+int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        const float* rotations, const float* cov3D_precomp, void* geom, void* binning, int64_t R_cap,
+                        void* img, float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                        uint32_t* num_rendered_host, void* stream) {
+  int rc = skgs_raster_forward_geometry(s, P, M, means3D, shs, colors_precomp, opacities, scales, rotations,
+                                        cov3D_precomp, geom, radii, nullptr, stream);
+  if (rc) return rc;
+  return skgs_raster_forward_render(s, P, geom, binning, R_cap, 0, img, radii, out_color, out_depth, out_alpha,
+                                    num_rendered_host, stream);
+}
+
+int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* scales, const float* rotations,
+                         const float* cov3D_precomp, const int32_t* radii, void* geom, const void* binning,
+                         int64_t R_cap, const void* img, const float* dL_dcolor, const float* dL_ddepth,
+                         const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
+                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                         float* dL_dcov3D, void* stream) {
+  RasterParams rp;
+  int rc = fill_params(s, P, M, rp);
+  if (rc) return rc;
+  if (P == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(geom && img && dL_dcolor && radii && means3D, "NULL arena / dL_dcolor / radii / means3D");
+  SKGS_CHECK_ARG(R_cap == 0 || binning != nullptr, "binning arena is NULL");
+  SKGS_CHECK_ARG(dL_dmeans3D != nullptr, "dL_dmeans3D is required");
+  SKGS_CHECK_ARG(shs == nullptr || dL_dsh != nullptr, "dL_dsh is required when shs is given");
+  SKGS_CHECK_ARG(scales == nullptr || (dL_dscales != nullptr && dL_drotations != nullptr && rotations != nullptr),
+                 "dL_dscales / dL_drotations are required when scales/rotations are given");
+  SKGS_CHECK_ARG(cov3D_precomp == nullptr || dL_dcov3D != nullptr, "dL_dcov3D is required when cov3D_precomp is given");
+  skgs_raster_layout lay;
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, R_cap, &lay);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_composite_bwd(rp, (char*)geom, (const char*)binning, (const char*)img, lay, dL_dcolor, dL_ddepth,
+                            dL_dalpha, st);
+  if (rc) return rc;
+  return launch_preprocess_bwd(rp, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, (char*)geom,
+                               lay, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
+                               dL_drotations, dL_dcov3D, st);
+}
+
+}  // extern "C"

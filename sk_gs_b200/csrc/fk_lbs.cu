@@ -1,0 +1,770 @@
+// fk_lbs.cu - skeleton forward kinematics + linear blend skinning (+ output assembly) for sm_100a.
+//   fk_lbs_fwd_kernel : every CTA rebuilds the M joint transforms in shared memory (local transform, L pointer-jumping
+//                       rounds over the binary-lifting table, global transform) - M <= 1024 so this is cheaper than a
+//                       second launch - then streams Gaussians: brute-force K-nearest joints in registers, skinning
+//                       weights (4 modes), blend of mean / rotation / scale.  Joint table (t, R, dq, ds, pos) is read
+//                       from shared memory only; per-Gaussian traffic is one coalesced read of xyz (+K sp_W gathers)
+//                       and coalesced writes of the outputs.
+//   lbs_bwd_kernel    : per-Gaussian gradients, per-joint sums in shared memory, one global atomic set per CTA and joint
+//   fk_bwd_kernel     : single CTA, level-synchronous backward through the kinematic chain
+//   assemble_*        : the element-wise activations of networks/sk_gs.py:1192,1202-1203
+// Semantics: SURVEY.md App. A.1-A.3 (reference networks/sk_gs.py:193-206,751-774,1069-1150; lietorch algebra as in
+// my_ext/_C/include/lie.h:45-64,142-159,228-249).  Quaternions are (x,y,z,w).
+#include "common.cuh"
+
+namespace skgs {
+
+constexpr int MAXK = 8;
+constexpr int FK_THREADS = 256;
+// per-joint accumulator layout of the backward pass
+constexpr int NJ = 19;  // dt[3] dq[4] d(sk_d_rot)[4] d(sk_d_scale)[3] dj(d2)[3] d(radius)[1] d(weight)[1]
+
+struct Quat {
+  float x, y, z, w;
+};
+struct Vec3 {
+  float x, y, z;
+};
+
+__device__ __forceinline__ Quat q_normalize(Quat q) {
+  const float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  const float inv = 1.0f / n;
+  return {q.x * inv, q.y * inv, q.z * inv, q.w * inv};
+}
+__device__ __forceinline__ Quat q_mul(Quat a, Quat b) {
+  return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+          a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+__device__ __forceinline__ Quat q_conj(Quat a) { return {-a.x, -a.y, -a.z, a.w}; }
+__device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// p + w*2(v x p) + v x 2(v x p)   (lie.h:59-64)
+__device__ __forceinline__ Vec3 q_rotate(Quat q, Vec3 p) {
+  const Vec3 v = {q.x, q.y, q.z};
+  Vec3 uv = cross(v, p);
+  uv = {uv.x + uv.x, uv.y + uv.y, uv.z + uv.z};
+  const Vec3 c = cross(v, uv);
+  return {p.x + q.w * uv.x + c.x, p.y + q.w * uv.y + c.y, p.z + q.w * uv.z + c.z};
+}
+// gradient of G . rotate(q, p) w.r.t. the (unit) quaternion entries, polynomial form
+__device__ __forceinline__ Quat q_rotate_grad_q(Quat q, Vec3 p, Vec3 G) {
+  const Vec3 v = {q.x, q.y, q.z};
+  const Vec3 pxG = cross(p, G);
+  const Vec3 vxp = cross(v, p);
+  const float Gv = G.x * v.x + G.y * v.y + G.z * v.z;
+  const float vp = v.x * p.x + v.y * p.y + v.z * p.z;
+  const float Gp = G.x * p.x + G.y * p.y + G.z * p.z;
+  Quat g;
+  g.x = 2.f * q.w * pxG.x + 2.f * Gv * p.x + 2.f * vp * G.x - 4.f * Gp * v.x;
+  g.y = 2.f * q.w * pxG.y + 2.f * Gv * p.y + 2.f * vp * G.y - 4.f * Gp * v.y;
+  g.z = 2.f * q.w * pxG.z + 2.f * Gv * p.z + 2.f * vp * G.z - 4.f * Gp * v.z;
+  g.w = 2.f * (G.x * vxp.x + G.y * vxp.y + G.z * vxp.z);
+  return g;
+}
+// rotate by the inverse (conjugate) of a unit quaternion
+__device__ __forceinline__ Vec3 q_rotate_inv(Quat q, Vec3 p) { return q_rotate(q_conj(q), p); }
+// Jacobian-transpose of normalisation at u (|u| = n): (g - (g.uhat) uhat) / n
+__device__ __forceinline__ Quat q_normalize_bwd(Quat uhat, float n, Quat g) {
+  const float d = g.x * uhat.x + g.y * uhat.y + g.z * uhat.z + g.w * uhat.w;
+  const float inv = 1.0f / n;
+  return {(g.x - d * uhat.x) * inv, (g.y - d * uhat.y) * inv, (g.z - d * uhat.z) * inv, (g.w - d * uhat.w) * inv};
+}
+__device__ __forceinline__ Quat so3_exp(Vec3 phi) {  // lie.h:142-159
+  const float theta2 = phi.x * phi.x + phi.y * phi.y + phi.z * phi.z;
+  const float theta = sqrtf(theta2);
+  float imag, real;
+  if (theta < 1e-6f) {
+    const float theta4 = theta2 * theta2;
+    imag = 0.5f - (1.0f / 48.0f) * theta2 + (1.0f / 3840.0f) * theta4;
+    real = 1.0f - (1.0f / 8.0f) * theta2 + (1.0f / 384.0f) * theta4;
+  } else {
+    imag = sinf(0.5f * theta) / theta;
+    real = cosf(0.5f * theta);
+  }
+  return q_normalize({imag * phi.x, imag * phi.y, imag * phi.z, real});
+}
+
+__device__ __forceinline__ Quat load_q(const float* p) { return {p[0], p[1], p[2], p[3]}; }
+__device__ __forceinline__ Vec3 load_v(const float* p) { return {p[0], p[1], p[2]}; }
+
+// local rotation of joint a: normalize(sk_r) [left-multiplied by the repose delta]
+__device__ __forceinline__ Quat local_rotation(const skgs_skeleton& sk, int a) {
+  Quat r = q_normalize(load_q(sk.sk_r + 4 * a));
+  if (sk.sk_r_delta != nullptr) {
+    const Quat d = sk.sk_r_delta_dim == 3 ? so3_exp(load_v(sk.sk_r_delta + 3 * a))
+                                          : q_normalize(load_q(sk.sk_r_delta + 4 * a));
+    r = q_normalize(q_mul(d, r));
+  }
+  return r;
+}
+
+// shared-memory joint table used by the per-Gaussian loops
+struct JointTable {
+  float* pos;   // [M][3]
+  float* t;     // [M][3]
+  float* R;     // [M][9] row-major
+  float* dq;    // [M][4]
+  float* ds;    // [M][3]
+  float* aux;   // [M][2]  kernel modes: 1/(2 r^2), sigmoid(weight)
+};
+
+// Build sk_T for all joints in shared memory: se[2][M][7] ping-pong.  Returns index of the buffer holding the result.
+__device__ int fk_build(const skgs_skeleton& sk, float* se0, float* se1) {
+  const int M = sk.M;
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    float* o = se0 + 7 * a;
+    if (a == sk.root) {
+      o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
+      o[6] = 1.f;
+    } else {
+      const Quat r = local_rotation(sk, a);
+      const Vec3 j = load_v(sk.joints + 3 * a);
+      const Vec3 rj = q_rotate(r, {-j.x, -j.y, -j.z});
+      o[0] = j.x + rj.x; o[1] = j.y + rj.y; o[2] = j.z + rj.z;
+      o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
+    }
+  }
+  __syncthreads();
+  float* cur = se0;
+  float* nxt = se1;
+  for (int l = 0; l < sk.L; l++) {  // out = out[parents[:, l]] o out   (networks/sk_gs.py:199-200)
+    for (int a = threadIdx.x; a < M; a += blockDim.x) {
+      const int p = sk.parents[a * sk.L + l];
+      const float* A = cur + 7 * p;
+      const float* B = cur + 7 * a;
+      const Quat qa = q_normalize(load_q(A + 3)), qb = q_normalize(load_q(B + 3));
+      const Vec3 tb = q_rotate(qa, load_v(B));
+      const Quat qo = q_normalize(q_mul(qa, qb));
+      float* o = nxt + 7 * a;
+      o[0] = A[0] + tb.x; o[1] = A[1] + tb.y; o[2] = A[2] + tb.z;
+      o[3] = qo.x; o[4] = qo.y; o[5] = qo.z; o[6] = qo.w;
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (sk.g_tr != nullptr) {  // global_T * out  (:201-206)
+    const Quat qg = q_normalize(load_q(sk.g_tr + 3));
+    const Vec3 tg = load_v(sk.g_tr);
+    for (int a = threadIdx.x; a < M; a += blockDim.x) {
+      const float* B = cur + 7 * a;
+      const Quat qb = q_normalize(load_q(B + 3));
+      const Vec3 tb = q_rotate(qg, load_v(B));
+      const Quat qo = q_normalize(q_mul(qg, qb));
+      float* o = nxt + 7 * a;
+      o[0] = tg.x + tb.x; o[1] = tg.y + tb.y; o[2] = tg.z + tb.z;
+      o[3] = qo.x; o[4] = qo.y; o[5] = qo.z; o[6] = qo.w;
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  return cur == se0 ? 0 : 1;
+}
+
+__device__ __forceinline__ void quat_to_rows(Quat q, float* R) {
+  const float x = q.x, y = q.y, z = q.z, w = q.w;
+  R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - w * z); R[2] = 2.f * (x * z + w * y);
+  R[3] = 2.f * (x * y + w * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - w * x);
+  R[6] = 2.f * (x * z - w * y); R[7] = 2.f * (y * z + w * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+size_t fk_fwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 3 + 3 + 9 + 4 + 3 + 2) * sizeof(float); }
+
+__global__ void __launch_bounds__(FK_THREADS)
+fk_lbs_fwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, float* __restrict__ d_xyz,
+                  float* __restrict__ d_rot, float* __restrict__ d_scale, float* __restrict__ sk_T,
+                  float* __restrict__ weights, int64_t* __restrict__ indices) {
+  extern __shared__ float fsm[];
+  const int M = sk.M, K = sk.K;
+  float* se0 = fsm;
+  float* se1 = se0 + 7 * M;
+  JointTable jt;
+  jt.pos = se1 + 7 * M;
+  jt.t = jt.pos + 3 * M;
+  jt.R = jt.t + 3 * M;
+  jt.dq = jt.R + 9 * M;
+  jt.ds = jt.dq + 4 * M;
+  jt.aux = jt.ds + 3 * M;
+  const int res = fk_build(sk, se0, se1);
+  const float* T = res == 0 ? se0 : se1;
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    const float* Ta = T + 7 * a;
+    if (blockIdx.x == 0 && sk_T != nullptr)
+      for (int c = 0; c < 7; c++) sk_T[7 * a + c] = Ta[c];
+    jt.pos[3 * a] = sk.joints[3 * a]; jt.pos[3 * a + 1] = sk.joints[3 * a + 1]; jt.pos[3 * a + 2] = sk.joints[3 * a + 2];
+    jt.t[3 * a] = Ta[0]; jt.t[3 * a + 1] = Ta[1]; jt.t[3 * a + 2] = Ta[2];
+    quat_to_rows(q_normalize(load_q(Ta + 3)), jt.R + 9 * a);
+    for (int c = 0; c < 4; c++) jt.dq[4 * a + c] = sk.sk_d_rot[4 * a + c];
+    for (int c = 0; c < 3; c++) jt.ds[3 * a + c] = sk.sk_d_scale[3 * a + c];
+    if (sk.mode == SKGS_LBS_KERNEL || sk.mode == SKGS_LBS_WEIGHTED_KERNEL) {
+      const float r = expf(sk.sp_radius[a]);
+      jt.aux[2 * a] = 1.0f / (2.0f * r * r);
+      jt.aux[2 * a + 1] = sk.mode == SKGS_LBS_WEIGHTED_KERNEL ? sigmoidf(sk.sp_weight[a]) : 1.0f;
+    }
+  }
+  __syncthreads();
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    float bd[MAXK];
+    int bi[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; k++) {
+      bd[k] = k < K ? __int_as_float(0x7f800000) : -1.0f;  // slots >= K never accept
+      bi[k] = 0;
+    }
+    for (int a = 0; a < M; a++) {
+      const float dx = __fsub_rn(px, jt.pos[3 * a]), dy = __fsub_rn(py, jt.pos[3 * a + 1]),
+                  dz = __fsub_rn(pz, jt.pos[3 * a + 2]);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      // insertion into the ascending K-list (strict '<': ties keep the lower joint index first)
+#pragma unroll
+      for (int k = MAXK - 1; k >= 0; k--) {
+        if (k >= K) continue;
+        if (d2 < bd[k]) {
+          if (k + 1 < K) {
+            bd[k + 1] = bd[k];
+            bi[k + 1] = bi[k];
+          }
+          bd[k] = d2;
+          bi[k] = a;
+        }
+      }
+    }
+    // ---- weights
+    float w[MAXK];
+    float wsum = 0.f;
+    if (sk.mode == SKGS_LBS_W) {
+      float mx = -__int_as_float(0x7f800000);
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = sk.sp_W[(size_t)i * M + bi[k]];
+          mx = fmaxf(mx, w[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = expf(w[k] - mx);
+          wsum += w[k];
+        }
+    } else if (sk.mode == SKGS_LBS_DIST) {
+      float mx = -__int_as_float(0x7f800000);
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = -bd[k] / sk.temperature;
+          mx = fmaxf(mx, w[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = expf(w[k] - mx);
+          wsum += w[k];
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = expf(-bd[k] * jt.aux[2 * bi[k]]) * jt.aux[2 * bi[k] + 1] + 1e-7f;
+          wsum += w[k];
+        }
+    }
+    const float winv = 1.0f / wsum;
+    float ox = 0.f, oy = 0.f, oz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXK; k++)
+      if (k < K) {
+        const float wk = w[k] * winv;
+        w[k] = wk;
+        const int a = bi[k];
+        const float* R = jt.R + 9 * a;
+        const float yx = R[0] * px + R[1] * py + R[2] * pz + jt.t[3 * a];
+        const float yy = R[3] * px + R[4] * py + R[5] * pz + jt.t[3 * a + 1];
+        const float yz = R[6] * px + R[7] * py + R[8] * pz + jt.t[3 * a + 2];
+        ox += wk * yx; oy += wk * yy; oz += wk * yz;
+        r0 += wk * jt.dq[4 * a]; r1 += wk * jt.dq[4 * a + 1]; r2 += wk * jt.dq[4 * a + 2]; r3 += wk * jt.dq[4 * a + 3];
+        s0 += wk * jt.ds[3 * a]; s1 += wk * jt.ds[3 * a + 1]; s2 += wk * jt.ds[3 * a + 2];
+      }
+    d_xyz[3 * i] = ox - px; d_xyz[3 * i + 1] = oy - py; d_xyz[3 * i + 2] = oz - pz;
+    *reinterpret_cast<float4*>(d_rot + 4 * i) = make_float4(r0, r1, r2, r3);
+    d_scale[3 * i] = s0; d_scale[3 * i + 1] = s1; d_scale[3 * i + 2] = s2;
+#pragma unroll
+    for (int k = 0; k < MAXK; k++)
+      if (k < K) {
+        weights[(size_t)i * K + k] = w[k];
+        indices[(size_t)i * K + k] = (int64_t)bi[k];
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LBS backward: per-Gaussian gradients + per-joint accumulation
+// ------------------------------------------------------------------------------------------------------------------
+size_t lbs_bwd_smem_bytes(int M) { return (size_t)M * (3 + 7 + 4 + 3 + 2 + 1 + NJ) * sizeof(float); }
+
+__global__ void __launch_bounds__(FK_THREADS)
+lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const float* __restrict__ sk_T,
+               const float* __restrict__ weights, const int64_t* __restrict__ indices,
+               const float* __restrict__ g_dxyz, const float* __restrict__ g_drot, const float* __restrict__ g_dscale,
+               const float* __restrict__ g_w, float* __restrict__ dL_dsp_W, float* __restrict__ jacc /*[M][NJ]*/) {
+  extern __shared__ float bsm[];
+  const int M = sk.M, K = sk.K;
+  float* s_pos = bsm;             // [M][3]
+  float* s_T = s_pos + 3 * M;     // [M][7] (t, unit q)
+  float* s_dq = s_T + 7 * M;      // [M][4]
+  float* s_ds = s_dq + 4 * M;     // [M][3]
+  float* s_aux = s_ds + 3 * M;    // [M][2]
+  float* s_sig = s_aux + 2 * M;   // [M] sigmoid(weight)
+  float* s_acc = s_sig + M;       // [M][NJ]
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    for (int c = 0; c < 3; c++) s_pos[3 * a + c] = sk.joints[3 * a + c];
+    for (int c = 0; c < 3; c++) s_T[7 * a + c] = sk_T[7 * a + c];
+    const Quat q = q_normalize(load_q(sk_T + 7 * a + 3));
+    s_T[7 * a + 3] = q.x; s_T[7 * a + 4] = q.y; s_T[7 * a + 5] = q.z; s_T[7 * a + 6] = q.w;
+    for (int c = 0; c < 4; c++) s_dq[4 * a + c] = sk.sk_d_rot[4 * a + c];
+    for (int c = 0; c < 3; c++) s_ds[3 * a + c] = sk.sk_d_scale[3 * a + c];
+    s_aux[2 * a] = s_aux[2 * a + 1] = 0.f;
+    s_sig[a] = 1.f;
+    if (sk.mode == SKGS_LBS_KERNEL || sk.mode == SKGS_LBS_WEIGHTED_KERNEL) {
+      const float r = expf(sk.sp_radius[a]);
+      s_aux[2 * a] = 1.0f / (2.0f * r * r);
+      s_aux[2 * a + 1] = 1.0f / (r * r);
+      if (sk.mode == SKGS_LBS_WEIGHTED_KERNEL) s_sig[a] = sigmoidf(sk.sp_weight[a]);
+    }
+  }
+  for (int k = threadIdx.x; k < M * NJ; k += blockDim.x) s_acc[k] = 0.f;
+  __syncthreads();
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const Vec3 p = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    const Vec3 G = g_dxyz ? Vec3{g_dxyz[3 * i], g_dxyz[3 * i + 1], g_dxyz[3 * i + 2]} : Vec3{0.f, 0.f, 0.f};
+    const float4 gr = g_drot ? *reinterpret_cast<const float4*>(g_drot + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const Vec3 gs = g_dscale ? Vec3{g_dscale[3 * i], g_dscale[3 * i + 1], g_dscale[3 * i + 2]} : Vec3{0.f, 0.f, 0.f};
+    float w[MAXK], dw[MAXK];
+    int idx[MAXK];
+    float wdw = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXK; k++)
+      if (k < K) {
+        w[k] = weights[(size_t)i * K + k];
+        const int a = idx[k] = (int)indices[(size_t)i * K + k];
+        const float* Ta = s_T + 7 * a;
+        const Quat q = {Ta[3], Ta[4], Ta[5], Ta[6]};
+        const Vec3 y = q_rotate(q, p);
+        float d = G.x * (y.x + Ta[0]) + G.y * (y.y + Ta[1]) + G.z * (y.z + Ta[2]);
+        d += gr.x * s_dq[4 * a] + gr.y * s_dq[4 * a + 1] + gr.z * s_dq[4 * a + 2] + gr.w * s_dq[4 * a + 3];
+        d += gs.x * s_ds[3 * a] + gs.y * s_ds[3 * a + 1] + gs.z * s_ds[3 * a + 2];
+        if (g_w) d += g_w[(size_t)i * K + k];
+        dw[k] = d;
+        wdw += w[k] * d;
+        // per-joint sums: dt, dq (polynomial gradient, projected later in fk_bwd), d(sk_d_rot), d(sk_d_scale)
+        float* acc = s_acc + NJ * a;
+        const Vec3 wG = {w[k] * G.x, w[k] * G.y, w[k] * G.z};
+        const Quat gq = q_rotate_grad_q(q, p, wG);
+        atomicAdd(acc + 0, wG.x); atomicAdd(acc + 1, wG.y); atomicAdd(acc + 2, wG.z);
+        atomicAdd(acc + 3, gq.x); atomicAdd(acc + 4, gq.y); atomicAdd(acc + 5, gq.z); atomicAdd(acc + 6, gq.w);
+        atomicAdd(acc + 7, w[k] * gr.x); atomicAdd(acc + 8, w[k] * gr.y); atomicAdd(acc + 9, w[k] * gr.z);
+        atomicAdd(acc + 10, w[k] * gr.w);
+        atomicAdd(acc + 11, w[k] * gs.x); atomicAdd(acc + 12, w[k] * gs.y); atomicAdd(acc + 13, w[k] * gs.z);
+      }
+    // ---- through the weight function
+    if (sk.mode == SKGS_LBS_W) {
+      if (dL_dsp_W != nullptr) {
+        float* row = dL_dsp_W + (size_t)i * M;
+        for (int a = 0; a < M; a++) row[a] = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K) row[idx[k]] = w[k] * (dw[k] - wdw);
+      }
+    } else {
+      // u_k = e_k * s_k + 1e-7, w = u / S.  Recover S from the largest weight to avoid cancellation.
+      float d2[MAXK], e[MAXK];
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          const int a = idx[k];
+          const float dx = p.x - s_pos[3 * a], dy = p.y - s_pos[3 * a + 1], dz = p.z - s_pos[3 * a + 2];
+          d2[k] = dx * dx + dy * dy + dz * dz;
+          if (sk.mode == SKGS_LBS_DIST) {
+            e[k] = 0.f;
+          } else {
+            e[k] = expf(-d2[k] * s_aux[2 * a]);
+            S += e[k] * s_sig[a] + 1e-7f;
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          const int a = idx[k];
+          float* acc = s_acc + NJ * a;
+          float dd2;  // dL / d(d2_k)
+          if (sk.mode == SKGS_LBS_DIST) {
+            dd2 = -(w[k] * (dw[k] - wdw)) / sk.temperature;
+          } else {
+            const float du = (dw[k] - wdw) / S;
+            dd2 = -du * s_sig[a] * e[k] * s_aux[2 * a];
+            atomicAdd(acc + 17, du * s_sig[a] * e[k] * d2[k] * s_aux[2 * a + 1]);  // d / d(log radius)
+            if (sk.mode == SKGS_LBS_WEIGHTED_KERNEL)
+              atomicAdd(acc + 18, du * e[k] * s_sig[a] * (1.0f - s_sig[a]));       // d / d(weight logit)
+          }
+          atomicAdd(acc + 14, -2.0f * dd2 * (p.x - s_pos[3 * a]));
+          atomicAdd(acc + 15, -2.0f * dd2 * (p.y - s_pos[3 * a + 1]));
+          atomicAdd(acc + 16, -2.0f * dd2 * (p.z - s_pos[3 * a + 2]));
+        }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < M * NJ; k += blockDim.x) {
+    const float v = s_acc[k];
+    if (v != 0.f) atomicAdd(jacc + k, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// FK backward: one CTA.  Level-synchronous re-evaluation T_root = g, T_a = T_parent o L_a and its reverse sweep.
+// ------------------------------------------------------------------------------------------------------------------
+size_t fk_bwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 7 + 7 + 1) * sizeof(float) + 16; }
+
+__global__ void __launch_bounds__(1024)
+fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __restrict__ dL_dsk_T_direct,
+              float* __restrict__ dL_djoints, float* __restrict__ dL_dsk_r, float* __restrict__ dL_dsk_d_rot,
+              float* __restrict__ dL_dsk_d_scale, float* __restrict__ dL_dg_tr, float* __restrict__ dL_dsp_radius,
+              float* __restrict__ dL_dsp_weight) {
+  extern __shared__ float ksm[];
+  const int M = sk.M, L = sk.L;
+  float* s_L = ksm;              // local transforms [M][7]
+  float* s_T = s_L + 7 * M;      // global transforms [M][7]
+  float* s_gT = s_T + 7 * M;     // gradient w.r.t. global transforms [M][7]
+  float* s_gL = s_gT + 7 * M;    // gradient w.r.t. local transforms [M][7]
+  int* s_depth = reinterpret_cast<int*>(s_gL + 7 * M);
+  __shared__ int s_maxdepth;
+  if (threadIdx.x == 0) s_maxdepth = 0;
+  __syncthreads();
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    // depth by walking parents[:, 0]
+    int d = 0, f = a;
+    while (f != sk.root && d <= M) {
+      f = sk.parents[f * L];
+      d++;
+    }
+    s_depth[a] = d;
+    atomicMax(&s_maxdepth, d);
+    const Quat r = local_rotation(sk, a);
+    const Vec3 j = load_v(sk.joints + 3 * a);
+    const Vec3 rj = q_rotate(r, {-j.x, -j.y, -j.z});
+    float* o = s_L + 7 * a;
+    o[0] = j.x + rj.x; o[1] = j.y + rj.y; o[2] = j.z + rj.z; o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
+    for (int c = 0; c < 7; c++) {
+      s_gT[7 * a + c] = jacc[NJ * a + c] + (dL_dsk_T_direct ? dL_dsk_T_direct[7 * a + c] : 0.f);
+      s_gL[7 * a + c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int maxdepth = s_maxdepth;
+  Quat qg = {0.f, 0.f, 0.f, 1.f};
+  Vec3 tg = {0.f, 0.f, 0.f};
+  float ng = 1.f;
+  if (sk.g_tr != nullptr) {
+    const Quat raw = load_q(sk.g_tr + 3);
+    ng = sqrtf(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z + raw.w * raw.w);
+    qg = q_normalize(raw);
+    tg = load_v(sk.g_tr);
+  }
+  for (int lev = 0; lev <= maxdepth; lev++) {
+    for (int a = threadIdx.x; a < M; a += blockDim.x) {
+      if (s_depth[a] != lev) continue;
+      float* o = s_T + 7 * a;
+      if (lev == 0) {
+        o[0] = tg.x; o[1] = tg.y; o[2] = tg.z; o[3] = qg.x; o[4] = qg.y; o[5] = qg.z; o[6] = qg.w;
+      } else {
+        const int p = sk.parents[a * L];
+        const float* A = s_T + 7 * p;
+        const float* B = s_L + 7 * a;
+        const Quat qa = load_q(A + 3), qb = load_q(B + 3);
+        const Vec3 tb = q_rotate(qa, load_v(B));
+        const Quat qo = q_normalize(q_mul(qa, qb));
+        o[0] = A[0] + tb.x; o[1] = A[1] + tb.y; o[2] = A[2] + tb.z; o[3] = qo.x; o[4] = qo.y; o[5] = qo.z; o[6] = qo.w;
+      }
+    }
+    __syncthreads();
+  }
+  for (int lev = maxdepth; lev >= 1; lev--) {
+    for (int a = threadIdx.x; a < M; a += blockDim.x) {
+      if (s_depth[a] != lev) continue;
+      const int p = sk.parents[a * L];
+      const float* A = s_T + 7 * p;
+      const float* B = s_L + 7 * a;
+      const Quat qa = load_q(A + 3), qb = load_q(B + 3), qo = load_q(s_T + 7 * a + 3);
+      const Vec3 gt = load_v(s_gT + 7 * a);
+      // quaternion gradient arrives w.r.t. the stored unit quaternion: project onto its tangent space
+      const Quat gm = q_normalize_bwd(qo, 1.0f, load_q(s_gT + 7 * a + 3));
+      const Quat gqa_prod = q_mul(gm, q_conj(qb));   // d(qa qb)/dqa ^T gm
+      const Quat gqb = q_mul(q_conj(qa), gm);        // d(qa qb)/dqb ^T gm
+      const Quat gqa_rot = q_rotate_grad_q(qa, load_v(B), gt);
+      const Vec3 glt = q_rotate_inv(qa, gt);
+      float* gp = s_gT + 7 * p;
+      atomicAdd(gp + 0, gt.x); atomicAdd(gp + 1, gt.y); atomicAdd(gp + 2, gt.z);
+      atomicAdd(gp + 3, gqa_prod.x + gqa_rot.x); atomicAdd(gp + 4, gqa_prod.y + gqa_rot.y);
+      atomicAdd(gp + 5, gqa_prod.z + gqa_rot.z); atomicAdd(gp + 6, gqa_prod.w + gqa_rot.w);
+      float* gl = s_gL + 7 * a;
+      gl[0] = glt.x; gl[1] = glt.y; gl[2] = glt.z; gl[3] = gqb.x; gl[4] = gqb.y; gl[5] = gqb.z; gl[6] = gqb.w;
+    }
+    __syncthreads();
+  }
+  // root -> global transform
+  if (threadIdx.x == 0 && dL_dg_tr != nullptr) {
+    if (sk.g_tr != nullptr) {
+      const float* g = s_gT + 7 * sk.root;
+      const Quat gq = q_normalize_bwd(qg, ng, load_q(g + 3));
+      dL_dg_tr[0] = g[0]; dL_dg_tr[1] = g[1]; dL_dg_tr[2] = g[2];
+      dL_dg_tr[3] = gq.x; dL_dg_tr[4] = gq.y; dL_dg_tr[5] = gq.z; dL_dg_tr[6] = gq.w;
+    } else {
+      for (int c = 0; c < 7; c++) dL_dg_tr[c] = 0.f;
+    }
+  }
+  // local transform -> joints, sk_r ; plus the direct per-joint sums
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    const float* gl = s_gL + 7 * a;
+    Vec3 gj = {jacc[NJ * a + 14], jacc[NJ * a + 15], jacc[NJ * a + 16]};
+    Quat gr = {0.f, 0.f, 0.f, 0.f};
+    if (a != sk.root) {
+      const Quat r = load_q(s_L + 7 * a + 3);
+      const Vec3 j = load_v(sk.joints + 3 * a);
+      const Vec3 glt = load_v(gl);
+      // t = j + rotate(r, -j)
+      const Vec3 back = q_rotate_inv(r, glt);
+      gj.x += glt.x - back.x; gj.y += glt.y - back.y; gj.z += glt.z - back.z;
+      const Quat g1 = q_rotate_grad_q(r, {-j.x, -j.y, -j.z}, glt);
+      Quat g = {g1.x + gl[3], g1.y + gl[4], g1.z + gl[5], g1.w + gl[6]};
+      const Quat raw = load_q(sk.sk_r + 4 * a);
+      const float n0 = sqrtf(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z + raw.w * raw.w);
+      const Quat r0 = q_normalize(raw);
+      if (sk.sk_r_delta != nullptr) {
+        const Quat d = sk.sk_r_delta_dim == 3 ? so3_exp(load_v(sk.sk_r_delta + 3 * a))
+                                              : q_normalize(load_q(sk.sk_r_delta + 4 * a));
+        g = q_normalize_bwd(r, 1.0f, g);   // through normalize(d r0), |d r0| = 1
+        g = q_mul(q_conj(d), g);
+      }
+      gr = q_normalize_bwd(r0, n0, g);
+    }
+    if (dL_djoints) { dL_djoints[3 * a] = gj.x; dL_djoints[3 * a + 1] = gj.y; dL_djoints[3 * a + 2] = gj.z; }
+    if (dL_dsk_r) { dL_dsk_r[4 * a] = gr.x; dL_dsk_r[4 * a + 1] = gr.y; dL_dsk_r[4 * a + 2] = gr.z; dL_dsk_r[4 * a + 3] = gr.w; }
+    if (dL_dsk_d_rot)
+      for (int c = 0; c < 4; c++) dL_dsk_d_rot[4 * a + c] = jacc[NJ * a + 7 + c];
+    if (dL_dsk_d_scale)
+      for (int c = 0; c < 3; c++) dL_dsk_d_scale[3 * a + c] = jacc[NJ * a + 11 + c];
+    if (dL_dsp_radius) dL_dsp_radius[a] = jacc[NJ * a + 17];
+    if (dL_dsp_weight) dL_dsp_weight[a] = jacc[NJ * a + 18];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// output assembly (networks/sk_gs.py:1192,1202-1203; activations networks/gaussian_splatting.py:155-160)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void assemble_fwd_kernel(int P, const float* __restrict__ xyz, const float* __restrict__ scaling,
+                                    const float* __restrict__ rotation, const float* __restrict__ opacity,
+                                    const float* __restrict__ d_xyz, const float* __restrict__ d_rot,
+                                    const float* __restrict__ d_scale, float* __restrict__ points,
+                                    float* __restrict__ scales, float* __restrict__ rotations,
+                                    float* __restrict__ opacities) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int e = t0; e < 3 * P; e += stride) {
+    points[e] = xyz[e] + (d_xyz ? d_xyz[e] : 0.f);
+    scales[e] = expf(scaling[e]) + (d_scale ? d_scale[e] : 0.f);
+  }
+  for (int i = t0; i < P; i += stride) {
+    float4 r = *reinterpret_cast<const float4*>(rotation + 4 * i);
+    if (d_rot) {
+      const float4 d = *reinterpret_cast<const float4*>(d_rot + 4 * i);
+      r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+    }
+    const float n = fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w), 1e-12f);
+    *reinterpret_cast<float4*>(rotations + 4 * i) = make_float4(r.x / n, r.y / n, r.z / n, r.w / n);
+    opacities[i] = sigmoidf(opacity[i]);
+  }
+}
+
+__global__ void assemble_bwd_kernel(int P, const float* __restrict__ scaling, const float* __restrict__ rotation,
+                                    const float* __restrict__ opacity, const float* __restrict__ d_rot,
+                                    const float* __restrict__ gp, const float* __restrict__ gs,
+                                    const float* __restrict__ gr, const float* __restrict__ go,
+                                    float* __restrict__ dxyz, float* __restrict__ dscaling,
+                                    float* __restrict__ drotation, float* __restrict__ dopacity,
+                                    float* __restrict__ dd_xyz, float* __restrict__ dd_rot,
+                                    float* __restrict__ dd_scale) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int e = t0; e < 3 * P; e += stride) {
+    const float a = gp ? gp[e] : 0.f, b = gs ? gs[e] : 0.f;
+    if (dxyz) dxyz[e] = a;
+    if (dd_xyz) dd_xyz[e] = a;
+    if (dscaling) dscaling[e] = b * expf(scaling[e]);
+    if (dd_scale) dd_scale[e] = b;
+  }
+  for (int i = t0; i < P; i += stride) {
+    float4 r = *reinterpret_cast<const float4*>(rotation + 4 * i);
+    if (d_rot) {
+      const float4 d = *reinterpret_cast<const float4*>(d_rot + 4 * i);
+      r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+    }
+    const float4 g = gr ? *reinterpret_cast<const float4*>(gr + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float nn = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+    float4 o;
+    if (nn > 1e-12f) {
+      const float inv = 1.0f / nn;
+      const float ux = r.x * inv, uy = r.y * inv, uz = r.z * inv, uw = r.w * inv;
+      const float d = g.x * ux + g.y * uy + g.z * uz + g.w * uw;
+      o = make_float4((g.x - d * ux) * inv, (g.y - d * uy) * inv, (g.z - d * uz) * inv, (g.w - d * uw) * inv);
+    } else {
+      o = make_float4(g.x * 1e12f, g.y * 1e12f, g.z * 1e12f, g.w * 1e12f);
+    }
+    if (drotation) *reinterpret_cast<float4*>(drotation + 4 * i) = o;
+    if (dd_rot) *reinterpret_cast<float4*>(dd_rot + 4 * i) = o;
+    if (dopacity) {
+      const float s = sigmoidf(opacity[i]);
+      dopacity[i] = (go ? go[i] : 0.f) * s * (1.0f - s);
+    }
+  }
+}
+
+static int fk_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int check_skeleton(const skgs_skeleton* sk, int P) {
+  SKGS_CHECK_ARG(sk != nullptr, "skeleton is NULL");
+  SKGS_CHECK_ARG(sk->M >= 1 && sk->M <= 1024, "M=%d out of range [1,1024] (reference guard sp_gs_joint.cu:114)", sk->M);
+  SKGS_CHECK_ARG(sk->L >= 0 && sk->L <= 16, "L=%d out of range", sk->L);
+  SKGS_CHECK_ARG(sk->root >= 0 && sk->root < sk->M, "root=%d out of range", sk->root);
+  SKGS_CHECK_ARG(sk->K >= 1 && sk->K <= MAXK && sk->K <= sk->M, "K=%d must be in [1,%d] and <= M", sk->K, MAXK);
+  SKGS_CHECK_ARG(sk->mode >= 0 && sk->mode <= 3, "unknown LBS mode %d", sk->mode);
+  SKGS_CHECK_ARG(sk->joints && sk->sk_r && sk->sk_d_rot && sk->sk_d_scale, "joints/sk_r/sk_d_rot/sk_d_scale required");
+  SKGS_CHECK_ARG(sk->L == 0 || sk->parents, "parents required when L > 0");
+  SKGS_CHECK_ARG(sk->mode != SKGS_LBS_W || sk->sp_W || P == 0, "mode W needs sp_W");
+  SKGS_CHECK_ARG((sk->mode != SKGS_LBS_KERNEL && sk->mode != SKGS_LBS_WEIGHTED_KERNEL) || sk->sp_radius,
+                 "kernel modes need sp_radius");
+  SKGS_CHECK_ARG(sk->mode != SKGS_LBS_WEIGHTED_KERNEL || sk->sp_weight, "weighted_kernel needs sp_weight");
+  SKGS_CHECK_ARG(sk->mode != SKGS_LBS_DIST || sk->temperature > 0.f, "dist mode needs temperature > 0");
+  SKGS_CHECK_ARG(sk->sk_r_delta == nullptr || sk->sk_r_delta_dim == 3 || sk->sk_r_delta_dim == 4,
+                 "sk_r_delta_dim must be 3 or 4");
+  return SKGS_OK;
+}
+
+}  // namespace skgs
+
+using namespace skgs;
+
+extern "C" {
+
+int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, float* d_xyz, float* d_rot,
+                        float* d_scale, float* sk_T, float* weights, int64_t* indices, void* stream) {
+  int rc = check_skeleton(sk, P);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(P >= 0, "P < 0");
+  SKGS_CHECK_ARG(P == 0 || (xyz && d_xyz && d_rot && d_scale && weights && indices), "NULL per-Gaussian buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = fk_fwd_smem_bytes(sk->M);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    SKGS_CUDA(cudaFuncSetAttribute(fk_lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int grid = (P + FK_THREADS - 1) / FK_THREADS;
+  const int cap = fk_num_sms() * 4;
+  grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+  fk_lbs_fwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices);
+  SKGS_CHECK_LAUNCH("fk_lbs_fwd_kernel");
+  return SKGS_OK;
+}
+
+size_t skgs_fk_lbs_workspace_bytes(int32_t M) { return (size_t)(M > 0 ? M : 1) * NJ * sizeof(float); }
+
+int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, const float* sk_T, const float* weights,
+                         const int64_t* indices, const float* dL_dd_xyz, const float* dL_dd_rot,
+                         const float* dL_dd_scale, const float* dL_dsk_T, const float* dL_dweights, float* dL_djoints,
+                         float* dL_dsk_r, float* dL_dsk_d_rot, float* dL_dsk_d_scale, float* dL_dg_tr, float* dL_dsp_W,
+                         float* dL_dsp_radius, float* dL_dsp_weight, void* workspace, void* stream) {
+  int rc = check_skeleton(sk, P);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(workspace != nullptr && sk_T != nullptr, "workspace and sk_T are required");
+  SKGS_CHECK_ARG(P == 0 || (xyz && weights && indices), "NULL per-Gaussian buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* jacc = reinterpret_cast<float*>(workspace);
+  SKGS_CUDA(cudaMemsetAsync(jacc, 0, skgs_fk_lbs_workspace_bytes(sk->M), st));
+  if (P > 0) {
+    const size_t smem = lbs_bwd_smem_bytes(sk->M);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    int grid = (P + FK_THREADS - 1) / FK_THREADS;
+    const int cap = fk_num_sms() * 4;
+    grid = grid > cap ? cap : grid;
+    lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
+                                                   dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
+    SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
+  }
+  {
+    const size_t smem = fk_bwd_smem_bytes(sk->M);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      SKGS_CUDA(cudaFuncSetAttribute(fk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    int threads = ((sk->M + 31) / 32) * 32;
+    threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+    fk_bwd_kernel<<<1, threads, smem, st>>>(*sk, jacc, dL_dsk_T, dL_djoints, dL_dsk_r, dL_dsk_d_rot, dL_dsk_d_scale,
+                                            dL_dg_tr, dL_dsp_radius, dL_dsp_weight);
+    SKGS_CHECK_LAUNCH("fk_bwd_kernel");
+  }
+  return SKGS_OK;
+}
+
+int skgs_assemble_forward(int32_t P, const float* xyz, const float* scaling, const float* rotation,
+                          const float* opacity, const float* d_xyz, const float* d_rot, const float* d_scale,
+                          float* points, float* scales, float* rotations, float* opacities, void* stream) {
+  SKGS_CHECK_ARG(P >= 0, "P < 0");
+  if (P == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(xyz && scaling && rotation && opacity && points && scales && rotations && opacities, "NULL buffer");
+  int grid = (3 * P + 255) / 256;
+  const int cap = fk_num_sms() * 8;
+  grid = grid > cap ? cap : grid;
+  assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale,
+                                                             points, scales, rotations, opacities);
+  SKGS_CHECK_LAUNCH("assemble_fwd_kernel");
+  return SKGS_OK;
+}
+
+int skgs_assemble_backward(int32_t P, const float* scaling, const float* rotation, const float* opacity,
+                           const float* d_rot, const float* dL_dpoints, const float* dL_dscales,
+                           const float* dL_drotations, const float* dL_dopacities, float* dL_dxyz, float* dL_dscaling,
+                           float* dL_drotation, float* dL_dopacity, float* dL_dd_xyz, float* dL_dd_rot,
+                           float* dL_dd_scale, void* stream) {
+  SKGS_CHECK_ARG(P >= 0, "P < 0");
+  if (P == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(scaling && rotation && opacity, "NULL buffer");
+  int grid = (3 * P + 255) / 256;
+  const int cap = fk_num_sms() * 8;
+  grid = grid > cap ? cap : grid;
+  assemble_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, scaling, rotation, opacity, d_rot, dL_dpoints,
+                                                             dL_dscales, dL_drotations, dL_dopacities, dL_dxyz,
+                                                             dL_dscaling, dL_drotation, dL_dopacity, dL_dd_xyz,
+                                                             dL_dd_rot, dL_dd_scale);
+  SKGS_CHECK_LAUNCH("assemble_bwd_kernel");
+  return SKGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+"""Drop-in for the un-vendored `diff_gaussian_rasterization` module the reference imports
+(/root/reference/networks/renderer/gaussian_render_origin.py:7, gui.py:535; boundary B1 of SURVEY.md 8b).
+
+Same names and call shapes: `GaussianRasterizationSettings(image_height, image_width, tanfovx, tanfovy, bg,
+scale_modifier, viewmatrix, projmatrix, sh_degree, campos, prefiltered, debug)` as built at
+networks/gaussian_splatting.py:271-284, and `GaussianRasterizer(raster_settings)(means3D, means2D, shs, colors_precomp,
+opacities, scales, rotations (w,x,y,z), cov3D_precomp)` returning the 4-tuple `(image[3,H,W], radii int32[P],
+depth[1,H,W], alpha[1,H,W])` accepted at gaussian_render_origin.py:53-54.  The gradient of the screen-space means is
+delivered as the gradient of the `means2D` input ([P,3], z = 0), exactly how densification consumes it
+(networks/gaussian_splatting.py:503-513).
+
+Everything runs in the hand-written sm_100a kernels of libskgs_b200.so on torch's CURRENT stream; there is no
+PyTorch/CPU fallback.  Host synchronisation: none in the kernels; the wrapper waits only on an event recorded right
+after the preprocess+scan stage (to learn R and validate the binning capacity) while the rest of the forward is
+already queued - the GPU never idles, unlike the reference's blocking cudaMemcpy
+(my_ext/_C/src/nerf/gaussian_rasterizer_forward.cu:208-209).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: Tensor
+    scale_modifier: float
+    viewmatrix: Tensor
+    projmatrix: Tensor
+    sh_degree: int
+    campos: Tensor
+    prefiltered: bool = False
+    debug: bool = False
+
+
+# ------------------------------------------------------------------------------------------------- capacity policy
+class _Capacity:
+    """Binning-arena capacity estimate per (device, P, W, H): last observed R with 25 % head room."""
+
+    def __init__(self):
+        self.last = {}
+        self.growth = 1.25
+        self.fixed: Optional[int] = None  # set_fixed_capacity(): never look at R on the host (CUDA-graph friendly)
+
+    def get(self, key):
+        return self.last.get(key)
+
+    def put(self, key, R):
+        self.last[key] = int(R)
+
+
+_capacity = _Capacity()
+_pinned = {}
+
+
+def set_fixed_capacity(R_cap: Optional[int]):
+    """R_cap entries for every call and no host read-back at all (overflow => image invalid, header.overflow = 1)."""
+    _capacity.fixed = None if R_cap is None else int(R_cap)
+
+
+def _pinned_words(device) -> Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = torch.zeros(4, dtype=torch.int32).pin_memory()
+        _pinned[key] = buf
+    return buf
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _absent(t: Optional[Tensor]) -> bool:
+    """The reference encodes 'absent' both as None and as an empty tensor (networks/renderer/gaussian_render.py:257-267)."""
+    return t is None or t.numel() == 0
+
+
+class RasterState(NamedTuple):
+    """Opaque per-call state kept for backward (the analogue of geomBuffer/binningBuffer/imgBuffer + num_rendered,
+    networks/renderer/gaussian_render.py:19-31,112-117)."""
+    settings: object
+    keep: tuple
+    P: int
+    M: int
+    R_cap: int
+    geom: Tensor
+    binning: Tensor
+    img: Tensor
+    radii: Tensor
+    layout: object
+    num_rendered: int
+
+
+def _make_settings(rs: GaussianRasterizationSettings, device, quat_wxyz: bool, debug_flags: int = 0):
+    view, proj, campos = _f32c(rs.viewmatrix.to(device)), _f32c(rs.projmatrix.to(device)), _f32c(rs.campos.to(device))
+    bg = None if rs.bg is None else _f32c(rs.bg.to(device))
+    s = _lib.RasterSettings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+                            float(rs.scale_modifier), int(rs.sh_degree), int(quat_wxyz), int(bool(rs.prefiltered)),
+                            int(bool(rs.debug)) | debug_flags, view.data_ptr(), proj.data_ptr(), campos.data_ptr(),
+                            None if bg is None else bg.data_ptr())
+    return s, (view, proj, campos, bg)
+
+
+def layout_query(P: int, W: int, H: int, R_cap: int):
+    lay = _lib.RasterLayout()
+    _lib.check(_lib.lib().skgs_raster_layout_query(P, W, H, R_cap, C.byref(lay)), 'skgs_raster_layout_query')
+    return lay
+
+
+def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs=None, colors_precomp=None,
+                      scales=None, rotations=None, cov3D_precomp=None, quat_wxyz: bool = True, debug_flags: int = 0):
+    """Non-autograd forward.  Returns (color, depth, alpha, radii, RasterState)."""
+    L = _lib.lib()
+    if not means3D.is_cuda:
+        raise RuntimeError('means3D must be a CUDA tensor (sk_gs_b200 has no CPU path)')
+    device = means3D.device
+    means3D = _f32c(means3D)
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError('means3D must have dimensions (num_points, 3)')  # gaussian_rasterizer_forward.cu:271-273
+    P = means3D.shape[0]
+    shs = None if _absent(shs) else _f32c(shs)
+    colors_precomp = None if _absent(colors_precomp) else _f32c(colors_precomp)
+    scales = None if _absent(scales) else _f32c(scales)
+    rotations = None if _absent(rotations) else _f32c(rotations)
+    cov3D_precomp = None if _absent(cov3D_precomp) else _f32c(cov3D_precomp)
+    opacities = _f32c(opacities)
+    M = 0 if shs is None else int(shs.shape[1])
+    W, H = int(rs.image_width), int(rs.image_height)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device)
+        st = stream.cuda_stream
+        s, keep = _make_settings(rs, device, quat_wxyz, debug_flags)
+        lay0 = layout_query(P, W, H, 0)
+        geom = torch.empty(lay0.geom_bytes, dtype=torch.uint8, device=device)
+        img = torch.empty(lay0.img_bytes, dtype=torch.uint8, device=device)
+        radii = torch.empty(P, dtype=torch.int32, device=device)
+        color = torch.empty(3, H, W, dtype=torch.float32, device=device)
+        depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
+        alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
+        fixed = _capacity.fixed
+        words = None if fixed is not None else _pinned_words(device)
+        _lib.check(L.skgs_raster_forward_geometry(
+            C.byref(s), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(opacities),
+            _lib.ptr(scales), _lib.ptr(rotations), _lib.ptr(cov3D_precomp), geom.data_ptr(), radii.data_ptr(),
+            None if words is None else words.data_ptr(), st), 'skgs_raster_forward_geometry')
+        key = (device.index, P, W, H)
+        R_known = None
+        if fixed is not None:
+            R_cap = fixed
+        else:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            est = _capacity.get(key)
+            if est is None:  # first call for this shape: one blocking read of R, like the reference does every call
+                ev.synchronize()
+                R_known = int(words[0].item()) & 0xffffffff
+                est = R_known
+            R_cap = max(int(est * _capacity.growth) + 4096, 4096)
+        while True:
+            lay = layout_query(P, W, H, R_cap)
+            binning = torch.empty(lay.binning_bytes, dtype=torch.uint8, device=device)
+            hint = R_known if R_known is not None else (_capacity.get(key) or R_cap)
+            _lib.check(L.skgs_raster_forward_render(
+                C.byref(s), P, geom.data_ptr(), binning.data_ptr(), R_cap, int(hint), img.data_ptr(), radii.data_ptr(),
+                color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), None, st), 'skgs_raster_forward_render')
+            if fixed is not None:
+                R_known = -1
+                break
+            if R_known is None:
+                ev.synchronize()  # preprocess+scan finished long ago; everything after it is already queued
+                R_known = int(words[0].item()) & 0xffffffff
+            _capacity.put(key, R_known)
+            if R_known <= R_cap:
+                break
+            R_cap = int(R_known * _capacity.growth) + 4096  # under-estimated: redo binning + compositing
+    state = RasterState(s, keep + (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp), P, M,
+                        R_cap, geom, binning, img, radii, lay, R_known)
+    return color, depth, alpha, radii, state
+
+
+def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None):
+    """Returns dict of gradients (None where the input was absent)."""
+    L = _lib.lib()
+    (view, proj, campos, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp) = state.keep
+    device = means3D.device
+    P, M = state.P, state.M
+    dL_dcolor = _f32c(dL_dcolor)
+    dL_ddepth = None if dL_ddepth is None else _f32c(dL_ddepth)
+    dL_dalpha = None if dL_dalpha is None else _f32c(dL_dalpha)
+
+    def new(*shape):
+        return torch.empty(*shape, dtype=torch.float32, device=device)
+
+    g = {
+        'means3D': new(P, 3), 'means2D': new(P, 3), 'opacities': new(P, 1),
+        'shs': None if shs is None else new(P, M, 3),
+        'colors_precomp': None if colors_precomp is None else new(P, 3),
+        'scales': None if scales is None else new(P, 3),
+        'rotations': None if rotations is None else new(P, 4),
+        'cov3D_precomp': None if cov3D_precomp is None else new(P, 6),
+    }
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(L.skgs_raster_backward(
+            C.byref(state.settings), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(scales),
+            _lib.ptr(rotations), _lib.ptr(cov3D_precomp), state.radii.data_ptr(), state.geom.data_ptr(),
+            state.binning.data_ptr(), state.R_cap, state.img.data_ptr(), dL_dcolor.data_ptr(), _lib.ptr(dL_ddepth),
+            _lib.ptr(dL_dalpha), _lib.ptr(g['means3D']), _lib.ptr(g['means2D']), _lib.ptr(g['shs']),
+            _lib.ptr(g['colors_precomp']), _lib.ptr(g['opacities']), _lib.ptr(g['scales']), _lib.ptr(g['rotations']),
+            _lib.ptr(g['cov3D_precomp']), st), 'skgs_raster_backward')
+    return g
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                raster_settings, quat_wxyz):
+        color, depth, alpha, radii, state = rasterize_forward(raster_settings, means3D, opacities, shs, colors_precomp,
+                                                              scales, rotations, cov3D_precomp, quat_wxyz)
+        ctx.state = state
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        state = ctx.state
+        if state.P == 0:
+            return (None,) * 10
+        if g_color is None:
+            g_color = torch.zeros(3, state.settings.image_height, state.settings.image_width, device=state.radii.device)
+        g = rasterize_backward(state, g_color, g_depth, g_alpha)
+        ctx.state = None
+        return (g['means3D'], g['means2D'], g['shs'], g['colors_precomp'], g['opacities'], g['scales'],
+                g['rotations'], g['cov3D_precomp'], None, None)
+
+
+def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, quat_wxyz: bool = True):
+    return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings, quat_wxyz)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: Tensor) -> Tensor:
+        """Frustum test of the upstream module: p_view.z > 0.2 (gaussian_preprocess_colmap.cu:63-82)."""
+        with torch.no_grad():
+            V = self.raster_settings.viewmatrix.to(positions)
+            z = positions @ V[:3, 2] + V[3, 2]
+            return z > 0.2
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings, True)
