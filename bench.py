@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py - SK_GS hot path benchmark (FK + LBS + rasterize forward + backward), one JSON line per run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+Metric (BASELINE.json): train steps/s, one step = FK + LBS + assembly + preprocess + binning/sort + composite forward +
+full backward to the parameter gradients for ONE 800x800 view of the 100K-Gaussian / 32-joint scene (`c2`); with N > 1
+ranks every rank renders its own view of the same scene (view sharding, weak scaling) and the Gaussian + skeleton
+gradients are all-reduced with NCCL inside the step.  `value` = views processed by all ranks per second.
+
+Timing: W warm-up steps, then K steps; every step is bracketed by its own CUDA-event pair on the launching stream and a
+256 MiB memset between steps evicts L2 (excluded from the step time); ranks are aligned by a barrier + synchronize on
+both sides and the slowest rank's time counts.  `e2e` repeats the measurement through the public API with the per-step
+inputs (camera, joint rotations, upstream image gradient) coming from pinned HOST memory and the step's scalar result
+read back to the host inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def _dist():
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return world, rank, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def algorithmic_bytes(P, M, K, C, R, W, H, tiles):
+    """SURVEY.md 8(d) per-unit figures x the units one launch processes."""
+    nb = 6 if tiles <= 65536 else 7
+    return {
+        'fk_lbs_fwd_kernel': P * (12 + 4 * K + 40) + P * 12 * K,  # xyz in, K sp_W gathers, d_* out, weights+idx out
+        'assemble_fwd_kernel': P * (44 + 40 + 44),
+        'preprocess_scan_kernel': P * (44 + 12 * C + 75),
+        'duplicate_keys_kernel': P * 8 + R * 12,
+        'onesweep_pass_kernel': R * 24,  # per pass: read key+value, write key+value
+        'tile_ranges_kernel': R * 8,
+        'composite_fwd_kernel': R * 44 + H * W * 28,
+        'composite_bwd_kernel': R * (44 + 40) + H * W * (20 + 8),
+        'preprocess_bwd_kernel': P * (44 + 12 * C + 75 + 40) + P * (12 + 12 + 16 + 4 + 12 + 12 * C),
+        'assemble_bwd_kernel': P * (44 + 44 + 44),
+        'lbs_bwd_kernel': P * (40 + 12 + 12 * K) + P * 4 * M,
+        'fk_bwd_kernel': M * 44 * 4,
+        '_sort_passes': nb,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, world, rank, local):
+    import torch.distributed as dist
+    from sk_gs_b200 import _lib
+    from sk_gs_b200 import scene as S
+    from sk_gs_b200.pipeline import HotPath
+
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    cfg = S.CONFIGS[args.workload]
+    sc = S.make_scene(cfg, views=max(world, 1))
+    hp = HotPath(sc, dev, mode='W')
+    view = rank % len(sc.cameras)
+    H, W = cfg.H, cfg.W
+    gen = torch.Generator().manual_seed(1234 + rank)
+    dL_host = (torch.randn(3, H, W, generator=gen) / (3 * H * W)).pin_memory()
+    dL_dev = dL_host.to(dev)
+    # per-step host inputs of the e2e path: what the joint MLP would emit + the camera
+    joint_host = {n: getattr(sc, n).clone().pin_memory() for n in ('sk_r', 'sk_d_rot', 'sk_d_scale')}
+    cam = sc.cameras[view]
+    cam_host = {'viewmatrix': cam.viewmatrix.pin_memory(), 'projmatrix': cam.projmatrix.pin_memory(),
+                'campos': cam.campos.clone().pin_memory()}
+    rs = hp.settings[view]
+    result_host = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    params = list(hp.params.values())
+
+    def allreduce_grads(out):
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params] + [out['viewspace_points'].grad.reshape(-1)])
+        flat.mul_(1.0 / world)
+        dist.all_reduce(flat)
+        dist.all_reduce(out['radii'], op=dist.ReduceOp.MAX)
+
+    graph_state = {}
+
+    def step(e2e: bool):
+        if args.graph and world == 1:
+            return step_graph(e2e)
+        hp.zero_grad()
+        if e2e:
+            for n, t in joint_host.items():
+                hp.params[n].data.copy_(t, non_blocking=True)
+            rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
+            rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
+            rs.campos.copy_(cam_host['campos'], non_blocking=True)
+            dL = dL_dev
+            dL.copy_(dL_host, non_blocking=True)
+        else:
+            dL = dL_dev
+        out = hp.render(view)
+        img = out['images']
+        img.backward(dL)
+        allreduce_grads(out)
+        if e2e:
+            result_host.copy_((img.detach() * dL).sum().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(result_host[0])
+        return None
+
+    def step_graph(e2e: bool):
+        if 'g' not in graph_state:
+            graph_state['g'], graph_state['out'], graph_state['grads'] = hp.capture_step(view, dL_dev)
+        if e2e:
+            for n, t in joint_host.items():
+                hp.params[n].data.copy_(t, non_blocking=True)
+            rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
+            rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
+            rs.campos.copy_(cam_host['campos'], non_blocking=True)
+            dL_dev.copy_(dL_host, non_blocking=True)
+        graph_state['g'].replay()
+        if e2e:
+            img = graph_state['out']['images']
+            result_host.copy_((img.detach() * dL_dev).sum().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if hp.overflowed():
+                raise RuntimeError('binning capacity of the captured graph exceeded')
+            return float(result_host[0])
+        return None
+
+    def timed(e2e: bool, K: int, Wu: int):
+        for _ in range(Wu):
+            step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        launches0 = _lib.launch_count()
+        for _ in range(K):
+            flush.zero_()  # evict L2 (126 MB) between steps; outside the event pair
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(e2e)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - launches0
+        if args.graph and world == 1:
+            launches = K * getattr(hp, 'launches_per_step', 0)  # replays do not pass through the launch counter
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(True, args.steps, max(args.warmup, 3))
+
+    # ---- per-kernel device times for the roofline (separate pass, events around every launch)
+    kern = {}
+    R = 0
+    if rank == 0:
+        _lib.profile_enable(True)
+        nprof = 5
+        for _ in range(nprof):
+            flush.zero_()
+            out = hp.render(view)
+            out['images'].backward(dL_dev)
+        torch.cuda.synchronize()
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+        from sk_gs_b200 import diff_gaussian_rasterization as DGR
+        R = DGR._capacity.get((dev.index, cfg.P, W, H)) or 0
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        ab = algorithmic_bytes(cfg.P, cfg.M, sc.K, 16, R, W, H, tiles)
+        peak, peak_src = measured_peak_hbm()
+        for name, (n, us) in prof.items():
+            per = us / n
+            gbs = ab.get(name, 0) / (per * 1e-6) / 1e9 if per > 0 else 0.0
+            kern[name] = {'launches_per_step': n / nprof, 'us_per_launch': round(per, 3),
+                          'us_per_step': round(us / nprof, 3), 'algorithmic_GBps': round(gbs, 1),
+                          'frac_of_peak': round(gbs / peak, 4)}
+        dom = max(kern, key=lambda k: kern[k]['us_per_step'])
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['algorithmic_GBps'], 'peak': peak,
+                    'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['frac_of_peak'],
+                    'traffic': None,
+                    'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel; compositing is FP32-issue '
+                            'bound (about 145 flop/B), see DESIGN.md'}
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (same workload, 1 view)
+    cpu = cpu_baseline(args.workload, steps=args.cpu_steps) if (world == 1 and not args.no_cpu) else None
+    K = args.steps
+    line = {
+        'metric': 'train_steps_per_sec (FK+LBS+render fwd+bwd, one 800x800 view per step)',
+        'value': round(world * K / (ms_dev * 1e-3), 2), 'unit': 'steps/s', 'n_gpus': world, 'steps': K,
+        'warmup': args.warmup, 'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{cfg.name}: {cfg.P} Gaussians, {cfg.M} joints, {W}x{H}, 1 view per GPU, SH degree 3, '
+                               f'K=5 LBS mode W, fwd+bwd', 'num_rendered': R, 'views_per_step': world,
+                   'parallelism': f'view-sharded dp{world}' + (' + NCCL grad allreduce' if world > 1 else ''),
+                   'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs',
+                   'launch': 'CUDA graph replay (fixed binning capacity, overflow flag checked)' if (args.graph and world == 1)
+                   else 'eager launches'},
+        'clocks': clocks,
+        'e2e': {'value': round(world * K / (ms_e2e * 1e-3), 2), 'unit': 'steps/s',
+                'ms_per_step': round(ms_e2e / K, 4),
+                'h2d_bytes_per_step': int(dL_host.numel() * 4 + sum(t.numel() for t in joint_host.values()) * 4 +
+                                          sum(t.numel() for t in cam_host.values()) * 4),
+                'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'kernels': kern,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(workload: str, steps: int = 2, threads: int = 0):
+    """Oracle port (torch FK/LBS + C rasterizer) on the host cores: `steps` full fwd+bwd steps of the same workload."""
+    from oracle import raster as OR
+    from sk_gs_b200 import scene as S
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from skgs_test_util import np32, oracle_deform, oracle_settings
+    import numpy as np
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    OR.set_num_threads(cores)
+    cfg = S.CONFIGS[workload]
+    sc = S.make_scene(cfg, views=1)
+    s = oracle_settings(sc.cameras[0])
+    rng = np.random.default_rng(0)
+    dC = (rng.standard_normal((3, cfg.H, cfg.W)) / (3 * cfg.H * cfg.W)).astype(np.float32)
+
+    def one():
+        net, sk_out, leaves = oracle_deform(sc, requires_grad=True)
+        img, g, b = OR.render_forward(s, np32(net['points']), np32(net['opacity']), np32(net['scales']),
+                                      np32(net['rotations']), np32(net['sh_features']))
+        gr = OR.render_backward(s, g, b, img, dC, np32(net['points']), np32(net['scales']), np32(net['rotations']),
+                                np32(net['sh_features']))
+        # back through assembly + LBS + FK with torch autograd
+        torch.autograd.backward(
+            [net['points'], net['scales'], net['rotations'], net['opacity'], net['sh_features']],
+            [torch.from_numpy(gr.dL_dmeans3D), torch.from_numpy(gr.dL_dscales), torch.from_numpy(gr.dL_drotations),
+             torch.from_numpy(gr.dL_dopacity).reshape(-1, 1), torch.from_numpy(gr.dL_dsh)])
+        return b.R
+
+    one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return {'value': round(steps / dt, 4), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{steps} full fwd+bwd steps of {cfg.name} after 1 warm-up, oracle/fk_lbs.py (torch, {cores} threads)'
+                      f' + oracle/raster_oracle.c (OpenMP, {OR.num_threads()} threads)'}
+
+
+def run_reference(args, world, rank, local):
+    """Reference arm.  The reference has NO CPU implementation of this path: its rasterizer is a CUDA extension.  When the
+    extension compiled here from /root/reference (oracle/_ref) is loadable and a GPU is present, it is what runs
+    (kind "reference", device cuda) with the torch-op FK/LBS of oracle/fk_lbs.py on the GPU; otherwise the oracle port on
+    the host cores (kind "port").  --ref-device cpu forces the latter."""
+    if rank != 0:
+        return
+    from oracle import ref_ext
+    use_gpu = args.ref_device != 'cpu' and torch.cuda.is_available() and ref_ext.available()
+    K = args.steps
+    if not use_gpu:
+        steps = min(K, args.cpu_steps)
+        cpu = cpu_baseline(args.workload, steps=steps)
+        from sk_gs_b200 import scene as S
+        cfg = S.CONFIGS[args.workload]
+        line = {'impl': 'reference', 'metric': 'train_steps_per_sec (FK+LBS+render fwd+bwd, one 800x800 view per step)',
+                'value': cpu['value'], 'unit': 'steps/s', 'n_gpus': world, 'steps': steps, 'warmup': 1,
+                'ms_per_step': round(1000.0 / cpu['value'], 3), 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': cfg.name},
+                'cpu_baseline': cpu, 'e2e': {'value': cpu['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0,
+                                             'd2h_bytes_per_step': 0}}
+        print(json.dumps(line), flush=True)
+        return
+    from oracle import fk_lbs as OF
+    from sk_gs_b200 import scene as S
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    cfg = S.CONFIGS[args.workload]
+    sc = S.make_scene(cfg, views=1)
+    cam = sc.cameras[0]
+    names = ['xyz', 'scaling', 'rotation', 'opacity', 'f_dc', 'f_rest', 'sp_W', 'joints', 'sk_r', 'sk_d_rot',
+             'sk_d_scale', 'g_tr']
+    p = {n: getattr(sc, n).to(dev).clone().requires_grad_(True) for n in names}
+    parents = sc.parents.to(dev).long()
+    H, W = cfg.H, cfg.W
+    gen = torch.Generator().manual_seed(1234)
+    dL_host = (torch.randn(3, H, W, generator=gen) / (3 * H * W)).pin_memory()
+    dL_dev = dL_host.to(dev)
+    joint_host = {n: getattr(sc, n).clone().pin_memory() for n in ('sk_r', 'sk_d_rot', 'sk_d_scale')}
+    result_host = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(e2e):
+        for t in p.values():
+            t.grad = None
+        if e2e:
+            for n, t in joint_host.items():
+                p[n].data.copy_(t, non_blocking=True)
+            dL_dev.copy_(dL_host, non_blocking=True)
+        out = OF.sk_stage(p['xyz'], p['joints'], p['sk_r'], p['sk_d_rot'], p['sk_d_scale'], p['g_tr'], parents, sc.root,
+                          K=sc.K, mode='W', sp_W=p['sp_W'])
+        pts, scl, rot, op, sh = OF.assemble(p['xyz'], p['scaling'], p['rotation'], p['opacity'], p['f_dc'], p['f_rest'],
+                                            *out[:3])
+        r = ref_ext.render(pts, op, scl, rot, sh, cam)
+        r['images'].backward(dL_dev)
+        if e2e:
+            result_host.copy_((r['images'].detach() * dL_dev).sum().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def timed(e2e, K, Wu):
+        for _ in range(Wu):
+            step(e2e)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(e2e)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    ms_dev = timed(False, K, args.warmup)
+    ms_e2e = timed(True, K, max(args.warmup, 3))
+    line = {'impl': 'reference', 'metric': 'train_steps_per_sec (FK+LBS+render fwd+bwd, one 800x800 view per step)',
+            'value': round(K / (ms_dev * 1e-3), 2), 'unit': 'steps/s', 'n_gpus': 1, 'steps': K, 'warmup': args.warmup,
+            'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{cfg.name}: {cfg.P} Gaussians, {cfg.M} joints, {W}x{H}, 1 view, fwd+bwd',
+                       'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs'},
+            'cpu_baseline': {'value': round(K / (ms_dev * 1e-3), 2), 'unit': 'steps/s', 'cores': 0, 'kind': 'reference',
+                             'device': 'cuda',
+                             'sample': "the reference's own CUDA rasterizer (my_ext/_C/src/nerf/gaussian_*.cu compiled "
+                                       'unmodified into oracle/_ref, colmap=True) + torch-op FK/LBS on the GPU; the '
+                                       'reference has no CPU implementation of this path'},
+            'e2e': {'value': round(K / (ms_e2e * 1e-3), 2), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e / K, 4),
+                    'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2')
+    ap.add_argument('--ref-device', default='auto', choices=['auto', 'cpu', 'cuda'])
+    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graph', dest='graph', action='store_false',
+                    help='launch every step eagerly instead of replaying a captured CUDA graph')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    world, rank, local = _dist()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29511')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    try:
+        if args.impl == 'reference':
+            run_reference(args, world, rank, local)
+        else:
+            run_ours(args, world, rank, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -53,6 +53,12 @@ SKGS_API int skgs_built_for_sm(void);
 /* number of kernels launched by this process through the library so far (bench.py's `gpu_launches`) */
 SKGS_API uint64_t skgs_launch_count(void);
 
+/* Optional per-kernel device timing: while enabled, every kernel launched through the library is bracketed by a
+ * CUDA-event pair on its own stream.  skgs_profile_enable(0|1) also clears the records; skgs_profile_collect
+ * synchronises the recorded events and writes one line per kernel name: "<name> <launches> <total microseconds>". */
+SKGS_API void skgs_profile_enable(int on);
+SKGS_API int skgs_profile_collect(char* buf, size_t cap);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Rasterizer
  * ------------------------------------------------------------------------------------------------------------- */
@@ -90,7 +96,7 @@ typedef struct skgs_raster_layout {
   size_t tiles_touched;  /* uint32 [P] */
   size_t point_offsets;  /* uint32 [P]   inclusive prefix sum of tiles_touched */
   size_t scan_state;     /* uint64 [ceil(P/256)+1] look-back words of the fused scan */
-  size_t geom_grads;     /* float  [P][12] packed backward accumulators (see skgs_raster_backward) */
+  size_t geom_grads;     /* float  [P][12] packed backward accumulators: mean2D.xy conic.abc opacity depth - rgb - */
   /* binning (capacity R_cap entries) */
   size_t keys_unsorted;  /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */
   size_t vals_unsorted;  /* uint32 [R_cap] */
@@ -102,6 +108,8 @@ typedef struct skgs_raster_layout {
   size_t ranges;         /* uint2  [tiles] */
   size_t n_contrib;      /* uint32 [H*W] */
   size_t final_T;        /* float  [H*W] */
+  size_t tile_order;     /* uint32 [tiles]  tiles by decreasing list length (work order of the compositing kernels) */
+  size_t work_counters;  /* uint32 [2]      work tickets of the forward / backward compositing kernels */
 } skgs_raster_layout;
 
 /* Lives at geom + layout.header; written on the device, never read by the library on the host. */

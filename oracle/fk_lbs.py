@@ -141,7 +141,7 @@ def skeleton_warp_jump(local_T: Tensor, g_tr: Optional[Tensor], parents: Tensor,
     """`skeleton_warp_SE3` (:193-206): L rounds of pointer jumping, then left-multiply by the global transform."""
     out = local_T.clone()
     ident = out.new_tensor([0, 0, 0, 0, 0, 0, 1.0])
-    mask = torch.zeros(out.shape[0], 1, dtype=torch.bool)
+    mask = torch.zeros(out.shape[0], 1, dtype=torch.bool, device=out.device)
     mask[root] = True
     out = torch.where(mask, ident, out)
     for lv in range(parents.shape[1]):

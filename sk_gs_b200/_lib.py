@@ -26,7 +26,7 @@ class RasterSettings(C.Structure):
 _LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
                   'rgbd', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads', 'keys_unsorted',
                   'vals_unsorted', 'keys_sorted', 'point_list', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
-                  'final_T']
+                  'final_T', 'tile_order', 'work_counters']
 
 
 class RasterLayout(C.Structure):
@@ -51,6 +51,8 @@ _SIGNATURES = {
     'skgs_abi_version': (C.c_int, []),
     'skgs_built_for_sm': (C.c_int, []),
     'skgs_launch_count': (C.c_uint64, []),
+    'skgs_profile_enable': (None, [C.c_int]),
+    'skgs_profile_collect': (C.c_int, [C.c_char_p, C.c_size_t]),
     'skgs_raster_layout_query': (C.c_int, [_i32, _i32, _i32, _i64, C.POINTER(RasterLayout)]),
     'skgs_raster_forward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 8 + [_vp, _i64, _vp] +
                             [_vp] * 6),
@@ -98,6 +100,21 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(lib().skgs_launch_count())
+
+
+def profile_enable(on: bool):
+    lib().skgs_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """{kernel name: (launches, total microseconds)} recorded since profile_enable(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().skgs_profile_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, us = line.split()
+        out[name] = (int(n), float(us))
+    return out
 
 
 def ptr(t):

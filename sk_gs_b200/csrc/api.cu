@@ -4,6 +4,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,6 +23,28 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing -------------------------------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(const char* name, cudaStream_t st) {
+  ProfRec r{name, nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, st);
+}
 
 int sort_passes(int gx, int gy);
 
@@ -83,6 +109,47 @@ int skgs_abi_version(void) { return 1; }
 int skgs_built_for_sm(void) { return 100; }
 uint64_t skgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+void skgs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+
+int skgs_profile_collect(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    auto it = agg.find(r.name);
+    if (it == agg.end()) {
+      order.push_back(r.name);
+      agg[r.name] = {1, (double)ms};
+    } else {
+      it->second.first++;
+      it->second.second += ms;
+    }
+  }
+  std::string out;
+  char line[256];
+  for (auto& n : order) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second * 1000.0);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int)out.size();
+}
+
 int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skgs_raster_layout* out) {
   SKGS_CHECK_ARG(out != nullptr, "layout is NULL");
   SKGS_CHECK_ARG(P >= 0 && W > 0 && H > 0 && R_cap >= 0, "bad sizes P=%d W=%d H=%d R_cap=%lld", P, W, H,
@@ -133,6 +200,8 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   out->ranges = take((size_t)gx * gy * 8);
   out->n_contrib = take((size_t)W * H * 4);
   out->final_T = take((size_t)W * H * 4);
+  out->tile_order = take((size_t)gx * gy * 4);
+  out->work_counters = take(2 * sizeof(uint32_t));
   out->img_bytes = o;
   return SKGS_OK;
 }
@@ -189,6 +258,8 @@ int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* g
   rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, phys, radii, R_cap, R_hint, num_rendered_host, st);
   if (rc) return rc;
   if (s->debug & 2) return SKGS_OK;  // test hook: stop after binning
+  rc = launch_tile_order(rp, (char*)img, lay, st);
+  if (rc) return rc;
   return launch_composite_fwd(rp, (char*)geom, (char*)binning, (char*)img, lay, out_color, out_depth, out_alpha, st);
 }
 

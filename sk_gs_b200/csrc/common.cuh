@@ -18,6 +18,22 @@ constexpr int TILE_PIX = TILE * TILE;
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-kernel device timing (skgs_profile_enable): a CUDA-event pair around every launch on the launching
+// stream.  Off by default; bench.py turns it on only for its roofline pass, never for the throughput pass.
+bool prof_enabled();
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* name, cudaStream_t s) : st(s), on(prof_enabled()) {
+    if (on) prof_begin(name, st);
+  }
+  ~ProfScope() {
+    if (on) prof_end(st);
+  }
+};
+
 #define SKGS_CHECK_ARG(cond, ...)            \
   do {                                       \
     if (!(cond)) {                           \
@@ -124,6 +140,7 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
                            uint32_t* num_rendered_host, cudaStream_t st);
 int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                    const int32_t* radii, int64_t R_cap, int64_t R_hint, uint32_t* num_rendered_host, cudaStream_t st);
+int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st);
 int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                          float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
 int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning, const char* img,

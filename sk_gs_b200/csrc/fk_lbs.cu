@@ -684,8 +684,11 @@ int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, fl
   int grid = (P + FK_THREADS - 1) / FK_THREADS;
   const int cap = fk_num_sms() * 4;
   grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
-  fk_lbs_fwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices);
+  {
+    ProfScope prof_("fk_lbs_fwd_kernel", st);
+    fk_lbs_fwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices);
   SKGS_CHECK_LAUNCH("fk_lbs_fwd_kernel");
+  }
   return SKGS_OK;
 }
 
@@ -713,9 +716,12 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     int grid = (P + FK_THREADS - 1) / FK_THREADS;
     const int cap = fk_num_sms() * 4;
     grid = grid > cap ? cap : grid;
-    lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
+    {
+      ProfScope prof_("lbs_bwd_kernel", st);
+      lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
                                                    dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
     SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
+    }
   }
   {
     const size_t smem = fk_bwd_smem_bytes(sk->M);
@@ -726,9 +732,12 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     }
     int threads = ((sk->M + 31) / 32) * 32;
     threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
-    fk_bwd_kernel<<<1, threads, smem, st>>>(*sk, jacc, dL_dsk_T, dL_djoints, dL_dsk_r, dL_dsk_d_rot, dL_dsk_d_scale,
+    {
+      ProfScope prof_("fk_bwd_kernel", st);
+      fk_bwd_kernel<<<1, threads, smem, st>>>(*sk, jacc, dL_dsk_T, dL_djoints, dL_dsk_r, dL_dsk_d_rot, dL_dsk_d_scale,
                                             dL_dg_tr, dL_dsp_radius, dL_dsp_weight);
     SKGS_CHECK_LAUNCH("fk_bwd_kernel");
+    }
   }
   return SKGS_OK;
 }
@@ -742,9 +751,12 @@ int skgs_assemble_forward(int32_t P, const float* xyz, const float* scaling, con
   int grid = (3 * P + 255) / 256;
   const int cap = fk_num_sms() * 8;
   grid = grid > cap ? cap : grid;
-  assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale,
+  {
+    ProfScope prof_("assemble_fwd_kernel", (cudaStream_t)stream);
+    assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale,
                                                              points, scales, rotations, opacities);
   SKGS_CHECK_LAUNCH("assemble_fwd_kernel");
+  }
   return SKGS_OK;
 }
 
@@ -759,11 +771,14 @@ int skgs_assemble_backward(int32_t P, const float* scaling, const float* rotatio
   int grid = (3 * P + 255) / 256;
   const int cap = fk_num_sms() * 8;
   grid = grid > cap ? cap : grid;
-  assemble_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, scaling, rotation, opacity, d_rot, dL_dpoints,
+  {
+    ProfScope prof_("assemble_bwd_kernel", (cudaStream_t)stream);
+    assemble_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, scaling, rotation, opacity, d_rot, dL_dpoints,
                                                              dL_dscales, dL_drotations, dL_dopacities, dL_dxyz,
                                                              dL_dscaling, dL_drotation, dL_dopacity, dL_dd_xyz,
                                                              dL_dd_rot, dL_dd_scale);
   SKGS_CHECK_LAUNCH("assemble_bwd_kernel");
+  }
   return SKGS_OK;
 }
 

@@ -1,8 +1,5 @@
 // raster_bwd.cu - backward half of the tile rasterizer for sm_100a:
-//   K6 composite_bwd_kernel  : per-tile back-to-front traversal; per-thread sums over its pixels, warp-shuffle
-//                              reduction, shared-memory accumulation per staged Gaussian, then ONE vector RED set
-//                              (3 x red.global.add.v4.f32) per (tile, Gaussian) instead of 9-13 scalar atomics per
-//                              (pixel, Gaussian) as in the reference (my_ext/_C/src/nerf/gaussian_render.cu:295-338)
+//   (K6 composite_bwd_kernel lives in composite.cu)
 //   K7 preprocess_bwd_kernel : conic -> cov2D -> cov3D -> (scale, rotation); mean2D / depth / SH colour -> mean3D; SH
 // Semantics: SURVEY.md App. A.7-A.8 (reference gaussian_render.cu:182-341, gaussian_preprocess_colmap.cu:240-481,
 // gaussian_rasterizer_backwrad.cu:26-127).  The contributing-pair tests (power, alpha) use the same contraction-proof
@@ -19,167 +16,7 @@ __device__ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
                                             0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                             -0.5900435899266435f};
 
-constexpr int CB_PPT = 4;
-constexpr int CB_THREADS = TILE_PIX / CB_PPT;  // 64
-constexpr int CB_WARPS = CB_THREADS / 32;
-constexpr int CB_BATCH = 64;
-constexpr int NGRAD = 12;  // packed per-Gaussian accumulators: mx my | ca cb cc op | r g b z | pad pad  (see header)
-
-__global__ void __launch_bounds__(CB_THREADS)
-composite_bwd_kernel(int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                     const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                     const float4* __restrict__ rgbd, const float* __restrict__ bg,
-                     const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
-                     const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth,
-                     const float* __restrict__ dL_dalpha_map, float* __restrict__ ggrad) {
-  __shared__ float4 s_g0[CB_BATCH];  // gx, gy, A', B'
-  __shared__ float4 s_g1[CB_BATCH];  // C', opacity, pmin, -
-  __shared__ float4 s_c[CB_BATCH];   // r, g, b, depth
-  __shared__ uint32_t s_id[CB_BATCH];
-  __shared__ float s_acc[CB_BATCH][NGRAD];
-  __shared__ uint32_t s_maxlast[CB_WARPS];
-  const int tile = blockIdx.x;
-  const int tx = tile % gx, ty = tile / gx;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int TPR = TILE / CB_PPT;
-  const int row = tid / TPR, col0 = (tid % TPR) * CB_PPT;
-  const int py = ty * TILE + row, px0 = tx * TILE + col0;
-  const float pyf = (float)py;
-  const uint2 range = ranges[tile];
-  const size_t HW = (size_t)H * W;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-  const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
-
-  float T[CB_PPT], Tfin[CB_PPT], tail[CB_PPT], dp0[CB_PPT], dp1[CB_PPT], dp2[CB_PPT], dD[CB_PPT], pxf[CB_PPT];
-  float ac0[CB_PPT], ac1[CB_PPT], ac2[CB_PPT], acd[CB_PPT], la[CB_PPT], lc0[CB_PPT], lc1[CB_PPT], lc2[CB_PPT],
-      ld[CB_PPT];
-  uint32_t last[CB_PPT];
-  uint32_t mymax = 0;
-#pragma unroll
-  for (int k = 0; k < CB_PPT; k++) {
-    pxf[k] = (float)(px0 + k);
-    const bool inside = (px0 + k < W) && (py < H);
-    const size_t pid = (size_t)py * W + px0 + k;
-    last[k] = inside ? n_contrib[pid] : 0u;
-    Tfin[k] = inside ? final_T[pid] : 0.f;
-    T[k] = Tfin[k];
-    dp0[k] = inside ? dL_dpix[pid] : 0.f;
-    dp1[k] = inside ? dL_dpix[HW + pid] : 0.f;
-    dp2[k] = inside ? dL_dpix[2 * HW + pid] : 0.f;
-    dD[k] = (inside && dL_ddepth) ? dL_ddepth[pid] : 0.f;
-    const float dA = (inside && dL_dalpha_map) ? dL_dalpha_map[pid] : 0.f;
-    tail[k] = bg0 * dp0[k] + bg1 * dp1[k] + bg2 * dp2[k] - dA;
-    ac0[k] = ac1[k] = ac2[k] = acd[k] = la[k] = lc0[k] = lc1[k] = lc2[k] = ld[k] = 0.f;
-    mymax = max(mymax, last[k]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-  if (lane == 0) s_maxlast[warp] = mymax;
-  __syncthreads();
-  uint32_t maxlast = 0;
-#pragma unroll
-  for (int w = 0; w < CB_WARPS; w++) maxlast = max(maxlast, s_maxlast[w]);
-  // positions >= maxlast contribute to no pixel of this tile
-  for (int top = (int)maxlast; top > 0; top -= CB_BATCH) {
-    const int nb = min(CB_BATCH, top);
-    __syncthreads();
-    for (int k = tid; k < nb; k += CB_THREADS) {
-      const uint32_t g = point_list[range.x + (uint32_t)(top - 1 - k)];
-      const float2 m = means2D[g];
-      const float4 co = conic_opacity[g];
-      const float pmin = co.w >= (1.0f / 255.0f) ? (-__logf(255.0f * co.w) - 1e-4f) : 1.0f;
-      s_g0[k] = make_float4(m.x, m.y, -0.5f * co.x, -co.y);
-      s_g1[k] = make_float4(-0.5f * co.z, co.w, pmin, 0.f);
-      s_c[k] = rgbd[g];
-      s_id[k] = g;
-    }
-    for (int k = tid; k < nb * NGRAD; k += CB_THREADS) (&s_acc[0][0])[k] = 0.f;
-    __syncthreads();
-    for (int j = 0; j < nb; j++) {
-      const uint32_t posn = (uint32_t)(top - 1 - j);  // position of this Gaussian in the tile's list
-      const float4 g0 = s_g0[j];
-      const float4 g1 = s_g1[j];
-      const float dy = __fsub_rn(g0.y, pyf);
-      const float bdy = __fmul_rn(g0.w, dy);
-      const float cdy2 = __fmul_rn(__fmul_rn(g1.x, dy), dy);
-      float pw[CB_PPT];
-      bool hit = false;
-#pragma unroll
-      for (int k = 0; k < CB_PPT; k++) {
-        const float dx = __fsub_rn(g0.x, pxf[k]);
-        pw[k] = pair_power(g0.z, dx, bdy, cdy2);
-        hit = hit || (posn < last[k] && pw[k] <= 0.0f && pw[k] >= g1.z);
-      }
-      if (!__any_sync(0xffffffffu, hit)) continue;
-      float a_mx = 0.f, a_my = 0.f, a_ca = 0.f, a_cb = 0.f, a_cc = 0.f, a_op = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f,
-            a_z = 0.f;
-      if (hit) {
-        const float4 c = s_c[j];
-        const float A = -2.0f * g0.z, B = -g0.w, Cc = -2.0f * g1.x, o = g1.y;
-#pragma unroll
-        for (int k = 0; k < CB_PPT; k++) {
-          if (!(posn < last[k] && pw[k] <= 0.0f && pw[k] >= g1.z)) continue;
-          const float G = skgs_exp(pw[k]);
-          const float alpha = fminf(0.99f, __fmul_rn(o, G));
-          if (alpha < 1.0f / 255.0f) continue;
-          const float one_m_a = 1.0f - alpha;
-          const float inv = __frcp_rn(one_m_a);
-          T[k] = T[k] * inv;
-          const float w = alpha * T[k];
-          ac0[k] = fmaf(la[k], lc0[k] - ac0[k], ac0[k]);
-          ac1[k] = fmaf(la[k], lc1[k] - ac1[k], ac1[k]);
-          ac2[k] = fmaf(la[k], lc2[k] - ac2[k], ac2[k]);
-          acd[k] = fmaf(la[k], ld[k] - acd[k], acd[k]);
-          lc0[k] = c.x; lc1[k] = c.y; lc2[k] = c.z; ld[k] = c.w;
-          float dL_dalpha = (c.x - ac0[k]) * dp0[k] + (c.y - ac1[k]) * dp1[k] + (c.z - ac2[k]) * dp2[k] +
-                            (c.w - acd[k]) * dD[k];
-          a_r = fmaf(w, dp0[k], a_r);
-          a_g = fmaf(w, dp1[k], a_g);
-          a_b = fmaf(w, dp2[k], a_b);
-          a_z = fmaf(w, dD[k], a_z);
-          dL_dalpha *= T[k];
-          la[k] = alpha;
-          dL_dalpha = fmaf(-Tfin[k] * inv, tail[k], dL_dalpha);
-          const float dL_dG = o * dL_dalpha;
-          const float dx = __fsub_rn(g0.x, pxf[k]);
-          const float gdx = G * dx, gdy = G * dy;
-          const float dG_ddelx = -gdx * A - gdy * B;
-          const float dG_ddely = -gdy * Cc - gdx * B;
-          a_mx = fmaf(dL_dG, dG_ddelx, a_mx);
-          a_my = fmaf(dL_dG, dG_ddely, a_my);
-          a_ca = fmaf(gdx * dx, dL_dG, a_ca);
-          a_cb = fmaf(gdx * dy, dL_dG, a_cb);
-          a_cc = fmaf(gdy * dy, dL_dG, a_cc);
-          a_op = fmaf(G, dL_dalpha, a_op);
-        }
-      }
-      a_mx = warp_sum(a_mx); a_my = warp_sum(a_my); a_ca = warp_sum(a_ca); a_cb = warp_sum(a_cb);
-      a_cc = warp_sum(a_cc); a_op = warp_sum(a_op); a_r = warp_sum(a_r); a_g = warp_sum(a_g);
-      a_b = warp_sum(a_b); a_z = warp_sum(a_z);
-      if (lane == 0) {
-        float* s = s_acc[j];
-        atomicAdd(s + 0, a_mx * ddelx_dx);
-        atomicAdd(s + 1, a_my * ddely_dy);
-        atomicAdd(s + 2, -0.5f * a_ca);
-        atomicAdd(s + 3, -0.5f * a_cb);
-        atomicAdd(s + 4, -0.5f * a_cc);
-        atomicAdd(s + 5, a_op);
-        atomicAdd(s + 6, a_r);
-        atomicAdd(s + 7, a_g);
-        atomicAdd(s + 8, a_b);
-        atomicAdd(s + 9, a_z);
-      }
-    }
-    __syncthreads();
-    // one vector RED set per (tile, Gaussian)
-    for (int k = tid; k < nb * 3; k += CB_THREADS) {
-      const int j = k / 3, q = k % 3;
-      const float* s = s_acc[j] + 4 * q;
-      if (s[0] != 0.f || s[1] != 0.f || s[2] != 0.f || s[3] != 0.f)
-        red_add_v4(ggrad + (size_t)s_id[j] * NGRAD + 4 * q, s[0], s[1], s[2], s[3]);
-    }
-  }
-}
+constexpr int NGRAD = 12;  // packed per-Gaussian accumulators (composite.cu): mx my ca cb | cc op z - | r g b -
 
 // ------------------------------------------------------------------------------------------------------------------
 // K7: preprocess backward
@@ -222,9 +59,9 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   }
   if (dL_dopacity) dL_dopacity[i] = vis ? g[5] : 0.f;
   if (dL_dcolors) {
-    dL_dcolors[3 * i] = vis ? g[6] : 0.f;
-    dL_dcolors[3 * i + 1] = vis ? g[7] : 0.f;
-    dL_dcolors[3 * i + 2] = vis ? g[8] : 0.f;
+    dL_dcolors[3 * i] = vis ? g[8] : 0.f;
+    dL_dcolors[3 * i + 1] = vis ? g[9] : 0.f;
+    dL_dcolors[3 * i + 2] = vis ? g[10] : 0.f;
   }
   if (!vis) {
     dL_dmeans3D[3 * i] = dL_dmeans3D[3 * i + 1] = dL_dmeans3D[3 * i + 2] = 0.f;
@@ -315,16 +152,16 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
     dmz += (Pm[8] * m_w - Pm[11] * mul1) * g[0] + (Pm[9] * m_w - Pm[11] * mul2) * g[1];
   }
   // ---- depth output: z_view = third row of the view rotation . mean
-  dmx += V[2] * g[9];
-  dmy += V[6] * g[9];
-  dmz += V[10] * g[9];
+  dmx += V[2] * g[6];
+  dmy += V[6] * g[6];
+  dmz += V[10] * g[6];
   // ---- SH backward (gaussian_rasterizer_backwrad.cu:26-127)
   if (shs != nullptr && dL_dsh != nullptr) {
     const float dox = mx - s_cam[0], doy = my - s_cam[1], doz = mz - s_cam[2];
     const float len = sqrtf(dox * dox + doy * doy + doz * doz);
     const float x = dox / len, y = doy / len, z = doz / len;
     const uint8_t cl = clamped[i];
-    float dRGB[3] = {(cl & 1) ? 0.f : g[6], (cl & 2) ? 0.f : g[7], (cl & 4) ? 0.f : g[8]};
+    float dRGB[3] = {(cl & 1) ? 0.f : g[8], (cl & 2) ? 0.f : g[9], (cl & 4) ? 0.f : g[10]};
     float sh[48], dsh[48];
     const float* sf = shs + (size_t)i * M3;
     if (M3 % 4 == 0) {
@@ -468,23 +305,6 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   }
 }
 
-int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning, const char* img,
-                         const skgs_raster_layout& lay, const float* dL_dcolor, const float* dL_ddepth,
-                         const float* dL_dalpha, cudaStream_t st) {
-  float* ggrad = reinterpret_cast<float*>(geom + lay.geom_grads);
-  SKGS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)rp.P * NGRAD * sizeof(float), st));
-  const int tiles = rp.gx * rp.gy;
-  if (tiles == 0 || rp.P == 0) return SKGS_OK;
-  composite_bwd_kernel<<<tiles, CB_THREADS, 0, st>>>(
-      rp.W, rp.H, rp.gx, reinterpret_cast<const uint2*>(img + lay.ranges),
-      reinterpret_cast<const uint32_t*>(binning + lay.point_list), reinterpret_cast<const float2*>(geom + lay.means2D),
-      reinterpret_cast<const float4*>(geom + lay.conic_opacity), reinterpret_cast<const float4*>(geom + lay.rgbd),
-      rp.bg, reinterpret_cast<const uint32_t*>(img + lay.n_contrib), reinterpret_cast<const float*>(img + lay.final_T),
-      dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
-  SKGS_CHECK_LAUNCH("composite_bwd_kernel");
-  return SKGS_OK;
-}
-
 int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           const int32_t* radii, char* geom, const skgs_raster_layout& lay, float* dL_dmeans3D,
@@ -493,11 +313,14 @@ int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const fl
   if (rp.P == 0) return SKGS_OK;
   (void)colors_precomp;
   const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom + lay.cov3D);
-  preprocess_bwd_kernel<<<(rp.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, st>>>(
+  {
+    ProfScope prof_("preprocess_bwd_kernel", st);
+    preprocess_bwd_kernel<<<(rp.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, st>>>(
       rp, means3D, shs, cov3D_precomp ? nullptr : scales, rotations, cov, radii,
       reinterpret_cast<const uint8_t*>(geom + lay.clamped), reinterpret_cast<const float*>(geom + lay.geom_grads),
       dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
   SKGS_CHECK_LAUNCH("preprocess_bwd_kernel");
+  }
   return SKGS_OK;
 }
 

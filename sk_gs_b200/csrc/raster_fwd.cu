@@ -6,8 +6,7 @@
 //   K3 onesweep_pass_kernel   : one kernel per 8-bit digit, chained-scan (decoupled look-back) across key tiles,
 //                               stable warp-level multi-split ranking (match.any), smem-staged coalesced scatter
 //   K4 tile_ranges_kernel     : [start, end) of each screen tile in the sorted list
-//   K5 composite_fwd_kernel   : per-tile front-to-back alpha compositing, smem-staged Gaussian batches, several pixels
-//                               per thread with hoisted row terms, conservative exponent cut-off, warp-ballot skipping
+//   (K5/K6 compositing kernels live in composite.cu)
 // Semantics follow SURVEY.md App. A.4-A.6 (reference: my_ext/_C/src/nerf/gaussian_preprocess_colmap.cu:155-224,
 // gaussian_rasterizer_forward.cu:45-94,203-241, gaussian_render.cu:16-112).  This file MUST be compiled with
 // -fmad=false (and without fast-math): plain '*' and '+' below are separately rounded, exactly like the CPU oracle.
@@ -536,117 +535,6 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, const skgs
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K5: composite forward.  One CTA per 16x16 tile, CF_THREADS threads, PPT horizontally adjacent pixels per thread.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int CF_PPT = 4;
-constexpr int CF_THREADS = TILE_PIX / CF_PPT;  // 64
-constexpr int CF_BATCH = 128;
-
-__global__ void __launch_bounds__(CF_THREADS)
-composite_fwd_kernel(int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                     const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                     const float4* __restrict__ rgbd, const float* __restrict__ bg, float* __restrict__ out_color,
-                     float* __restrict__ out_depth, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
-                     float* __restrict__ final_T) {
-  __shared__ float4 s_g0[CF_BATCH];  // gx, gy, A', B'
-  __shared__ float4 s_g1[CF_BATCH];  // C', opacity, pmin, -
-  __shared__ float4 s_c[CF_BATCH];   // r, g, b, depth
-  const int tile = blockIdx.x;
-  const int tx = tile % gx, ty = tile / gx;
-  const int tid = threadIdx.x;
-  constexpr int TPR = TILE / CF_PPT;  // threads per row
-  const int row = tid / TPR, col0 = (tid % TPR) * CF_PPT;
-  const int py = ty * TILE + row, px0 = tx * TILE + col0;
-  const float pyf = (float)py;
-  const uint2 range = ranges[tile];
-  const int total = (int)(range.y - range.x);
-
-  float T[CF_PPT], C0[CF_PPT], C1[CF_PPT], C2[CF_PPT], Dp[CF_PPT], pxf[CF_PPT];
-  uint32_t last[CF_PPT];
-  bool done[CF_PPT];
-#pragma unroll
-  for (int k = 0; k < CF_PPT; k++) {
-    T[k] = 1.0f; C0[k] = C1[k] = C2[k] = Dp[k] = 0.f; last[k] = 0;
-    pxf[k] = (float)(px0 + k);
-    done[k] = (px0 + k >= W) || (py >= H);
-  }
-
-  for (int b0 = 0; b0 < total; b0 += CF_BATCH) {
-    bool all_done = true;
-#pragma unroll
-    for (int k = 0; k < CF_PPT; k++) all_done = all_done && done[k];
-    if (__syncthreads_and(all_done)) break;
-    const int nb = min(CF_BATCH, total - b0);
-    for (int k = tid; k < nb; k += CF_THREADS) {
-      const uint32_t g = point_list[range.x + b0 + k];
-      const float2 m = means2D[g];
-      const float4 co = conic_opacity[g];
-      // alpha = o*exp(power) >= 1/255 needs power >= -log(255 o); the cut-off is conservative (margin 1e-4), the exact
-      // test on alpha is still applied to everything that passes it
-      const float pmin = co.w >= (1.0f / 255.0f) ? (-__logf(255.0f * co.w) - 1e-4f) : 1.0f;
-      s_g0[k] = make_float4(m.x, m.y, -0.5f * co.x, -co.y);
-      s_g1[k] = make_float4(-0.5f * co.z, co.w, pmin, 0.f);
-      s_c[k] = rgbd[g];
-    }
-    __syncthreads();
-    if (!all_done) {
-      for (int j = 0; j < nb; j++) {
-        const float4 g0 = s_g0[j];
-        const float4 g1 = s_g1[j];
-        const float dy = __fsub_rn(g0.y, pyf);
-        const float bdy = __fmul_rn(g0.w, dy);
-        const float cdy2 = __fmul_rn(__fmul_rn(g1.x, dy), dy);
-        float pw[CF_PPT];
-        bool hit = false;
-#pragma unroll
-        for (int k = 0; k < CF_PPT; k++) {
-          const float dx = __fsub_rn(g0.x, pxf[k]);
-          pw[k] = pair_power(g0.z, dx, bdy, cdy2);
-          hit = hit || (!done[k] && pw[k] <= 0.0f && pw[k] >= g1.z);
-        }
-        if (!hit) continue;
-        const float4 c = s_c[j];
-#pragma unroll
-        for (int k = 0; k < CF_PPT; k++) {
-          if (done[k] || pw[k] > 0.0f || pw[k] < g1.z) continue;
-          const float alpha = fminf(0.99f, __fmul_rn(g1.y, skgs_exp(pw[k])));
-          if (alpha < 1.0f / 255.0f) continue;
-          const float test_T = __fmul_rn(T[k], __fsub_rn(1.0f, alpha));
-          if (test_T < 0.0001f) {
-            done[k] = true;
-            continue;
-          }
-          const float w = __fmul_rn(alpha, T[k]);
-          C0[k] = __fmaf_rn(c.x, w, C0[k]);
-          C1[k] = __fmaf_rn(c.y, w, C1[k]);
-          C2[k] = __fmaf_rn(c.z, w, C2[k]);
-          Dp[k] = __fmaf_rn(c.w, w, Dp[k]);
-          T[k] = test_T;
-          last[k] = (uint32_t)(b0 + j + 1);
-        }
-      }
-    }
-  }
-  if (py < H) {
-    const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
-    const size_t HW = (size_t)H * W;
-#pragma unroll
-    for (int k = 0; k < CF_PPT; k++) {
-      if (px0 + k < W) {
-        const size_t pid = (size_t)py * W + px0 + k;
-        out_color[pid] = __fmaf_rn(T[k], bg0, C0[k]);
-        out_color[HW + pid] = __fmaf_rn(T[k], bg1, C1[k]);
-        out_color[2 * HW + pid] = __fmaf_rn(T[k], bg2, C2[k]);
-        out_depth[pid] = Dp[k];
-        out_alpha[pid] = __fsub_rn(1.0f, T[k]);
-        n_contrib[pid] = last[k];
-        final_T[pid] = T[k];
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------------------
 int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
@@ -658,7 +546,9 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
   // header and scan_state are adjacent in the arena: one memset resets the ticket, the flags and the counters
   SKGS_CUDA(cudaMemsetAsync(geom + lay.header, 0, lay.means2D - lay.header, st));
   if (rp.P > 0) {
-    preprocess_scan_kernel<<<nblocks, PRE_THREADS, 0, st>>>(
+    {
+      ProfScope prof_("preprocess_scan_kernel", st);
+      preprocess_scan_kernel<<<nblocks, PRE_THREADS, 0, st>>>(
         rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii,
         reinterpret_cast<float2*>(geom + lay.means2D), reinterpret_cast<float*>(geom + lay.depths),
         reinterpret_cast<float*>(geom + lay.cov3D), reinterpret_cast<float4*>(geom + lay.conic_opacity),
@@ -666,6 +556,7 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
         reinterpret_cast<uint32_t*>(geom + lay.tiles_touched), reinterpret_cast<uint32_t*>(geom + lay.point_offsets),
         reinterpret_cast<uint64_t*>(geom + lay.scan_state), hdr, nblocks);
     SKGS_CHECK_LAUNCH("preprocess_scan_kernel");
+    }
   }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -702,11 +593,14 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   uint32_t* vB = reinterpret_cast<uint32_t*>(binning + lay.point_list);
   uint32_t* hist = reinterpret_cast<uint32_t*>(binning + lay.sort_hist);
   uint32_t* status = reinterpret_cast<uint32_t*>(binning + lay.sort_status);
-  duplicate_keys_kernel<<<(rp.P + DUP_THREADS - 1) / DUP_THREADS, DUP_THREADS, 0, st>>>(
+  {
+    ProfScope prof_("duplicate_keys_kernel", st);
+    duplicate_keys_kernel<<<(rp.P + DUP_THREADS - 1) / DUP_THREADS, DUP_THREADS, 0, st>>>(
       rp.P, rp.gx, rp.gy, radii, reinterpret_cast<const float2*>(geom + lay.means2D),
       reinterpret_cast<const float*>(geom + lay.depths), reinterpret_cast<const uint32_t*>(geom + lay.point_offsets),
       kA, vA, hist, hdr, (uint32_t)R_cap, passes);
   SKGS_CHECK_LAUNCH("duplicate_keys_kernel");
+  }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   static bool attr_set = false;
@@ -721,10 +615,13 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   uint64_t *kin = kA, *kout = kB;
   uint32_t *vin = vA, *vout = vB;
   for (int p = 0; p < passes; p++) {
-    onesweep_pass_kernel<<<grid, OS_THREADS, sizeof(OnesweepSmem), st>>>(kin, vin, kout, vout, hdr, (uint32_t)R_cap,
+    {
+      ProfScope prof_("onesweep_pass_kernel", st);
+      onesweep_pass_kernel<<<grid, OS_THREADS, sizeof(OnesweepSmem), st>>>(kin, vin, kout, vout, hdr, (uint32_t)R_cap,
                                                                           hist + p * 256, status,
                                                                           &hdr->sort_ticket[p], 8 * p, (uint32_t)p);
     SKGS_CHECK_LAUNCH("onesweep_pass_kernel");
+    }
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
@@ -732,22 +629,11 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   // skgs_raster_layout_query already reports keys_sorted/point_list at the physical location of the final result.
   int rgrid = (int)((hint + 255) / 256);
   rgrid = rgrid < 1 ? 1 : (rgrid > 8 * num_sms() ? 8 * num_sms() : rgrid);
-  tile_ranges_kernel<<<rgrid, 256, 0, st>>>(kin, hdr, (uint32_t)R_cap, reinterpret_cast<uint2*>(img + lay.ranges));
+  {
+    ProfScope prof_("tile_ranges_kernel", st);
+    tile_ranges_kernel<<<rgrid, 256, 0, st>>>(kin, hdr, (uint32_t)R_cap, reinterpret_cast<uint2*>(img + lay.ranges));
   SKGS_CHECK_LAUNCH("tile_ranges_kernel");
-  return SKGS_OK;
-}
-
-int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
-                         float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
-  const int tiles = rp.gx * rp.gy;
-  if (tiles == 0) return SKGS_OK;
-  composite_fwd_kernel<<<tiles, CF_THREADS, 0, st>>>(
-      rp.W, rp.H, rp.gx, reinterpret_cast<const uint2*>(img + lay.ranges),
-      reinterpret_cast<const uint32_t*>(binning + lay.point_list), reinterpret_cast<const float2*>(geom + lay.means2D),
-      reinterpret_cast<const float4*>(geom + lay.conic_opacity), reinterpret_cast<const float4*>(geom + lay.rgbd),
-      rp.bg, out_color, out_depth, out_alpha, reinterpret_cast<uint32_t*>(img + lay.n_contrib),
-      reinterpret_cast<float*>(img + lay.final_T));
-  SKGS_CHECK_LAUNCH("composite_fwd_kernel");
+  }
   return SKGS_OK;
 }
 

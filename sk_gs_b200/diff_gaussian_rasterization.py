@@ -62,13 +62,20 @@ _pinned = {}
 
 
 def set_fixed_capacity(R_cap: Optional[int]):
-    """R_cap entries for every call and no host read-back at all (overflow => image invalid, header.overflow = 1)."""
+    """R_cap entries for every call and no host wait at all (CUDA-graph capturable).  If R exceeds R_cap the image of that
+    call is INVALID: header.overflow = 1, also copied asynchronously into `last_header_words(device)[3]`."""
     _capacity.fixed = None if R_cap is None else int(R_cap)
 
 
+def last_header_words(device) -> Tensor:
+    """Pinned host int32[4] = {R, num_visible, -, overflow} of the most recent forward on the current stream (valid after
+    that forward has completed on the device)."""
+    return _pinned_words(torch.device(device))
+
+
 def _pinned_words(device) -> Tensor:
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _pinned.get(key)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _pinned.get(key)  # one per device: allocating pinned memory is illegal during stream capture
     if buf is None:
         buf = torch.zeros(4, dtype=torch.int32).pin_memory()
         _pinned[key] = buf
@@ -151,11 +158,11 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
         depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
         alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
         fixed = _capacity.fixed
-        words = None if fixed is not None else _pinned_words(device)
+        words = _pinned_words(device)  # {R, num_visible, -, overflow}; in fixed mode it is written but never waited on
         _lib.check(L.skgs_raster_forward_geometry(
             C.byref(s), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(opacities),
             _lib.ptr(scales), _lib.ptr(rotations), _lib.ptr(cov3D_precomp), geom.data_ptr(), radii.data_ptr(),
-            None if words is None else words.data_ptr(), st), 'skgs_raster_forward_geometry')
+            words.data_ptr(), st), 'skgs_raster_forward_geometry')
         key = (device.index, P, W, H)
         R_known = None
         if fixed is not None:
@@ -175,7 +182,8 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
             hint = R_known if R_known is not None else (_capacity.get(key) or R_cap)
             _lib.check(L.skgs_raster_forward_render(
                 C.byref(s), P, geom.data_ptr(), binning.data_ptr(), R_cap, int(hint), img.data_ptr(), radii.data_ptr(),
-                color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), None, st), 'skgs_raster_forward_render')
+                color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), words.data_ptr() if fixed is not None else None,
+                st), 'skgs_raster_forward_render')
             if fixed is not None:
                 R_known = -1
                 break

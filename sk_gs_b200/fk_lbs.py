@@ -69,6 +69,11 @@ class _FkLbs(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w, _g_idx):
+        return _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w)
+
+
+def _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w):
+    if True:
         L = _lib.lib()
         (xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, sk_r_delta, sk_T, weights,
          indices) = ctx.keep
@@ -136,6 +141,11 @@ class _Assemble(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gp, gs, gr, go):
+        return _assemble_backward_impl(ctx, gp, gs, gr, go)
+
+
+def _assemble_backward_impl(ctx, gp, gs, gr, go):
+    if True:
         L = _lib.lib()
         scaling, rotation, opacity, d_rot = ctx.keep
         device = scaling.device
@@ -165,3 +175,40 @@ def assemble(_xyz, _scaling, _rotation, _opacity, d_xyz=None, d_rot=None, d_scal
     """points = _xyz + d_xyz, scales = exp(_scaling) + d_scale, rotations = normalize(_rotation + d_rot),
     opacity = sigmoid(_opacity)   (networks/sk_gs.py:1162-1163,1192,1202-1203; gaussian_splatting.py:155-160)."""
     return _Assemble.apply(_xyz, _scaling, _rotation, _opacity, d_xyz, d_rot, d_scale)
+
+
+# --------------------------------------------------------------------------------------------- raw (non-autograd) calls
+class _Ctx:
+    """Minimal stand-in for an autograd ctx so that the Function bodies can be driven by hand (HotPath.step_manual:
+    no autograd engine, no AccumulateGrad nodes -> CUDA-graph capturable and cheaper on the host)."""
+
+    def __init__(self, needs):
+        self.needs_input_grad = needs
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+def fk_lbs_forward_raw(xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, parents, root, K=5, mode='W', sp_W=None,
+                       sp_radius=None, sp_weight=None, temperature=1.0, sk_r_delta=None):
+    ctx = _Ctx([False, True, True, True, True, g_tr is not None, sp_W is not None, sp_radius is not None,
+                sp_weight is not None] + [False] * 6)
+    out = _FkLbs.forward(ctx, xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, root,
+                         K, mode, temperature, sk_r_delta)
+    return out, ctx
+
+
+def fk_lbs_backward_raw(ctx, g_dxyz=None, g_drot=None, g_dscale=None, g_skT=None, g_w=None):
+    """-> (d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight)"""
+    r = _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w)
+    return r[1:9]
+
+
+def assemble_forward_raw(xyz, scaling, rotation, opacity, d_xyz=None, d_rot=None, d_scale=None):
+    ctx = _Ctx([True] * 7)
+    return _Assemble.forward(ctx, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale), ctx
+
+
+def assemble_backward_raw(ctx, gp, gs, gr, go):
+    """-> (dxyz, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale)"""
+    return _assemble_backward_impl(ctx, gp, gs, gr, go)

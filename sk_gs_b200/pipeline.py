@@ -73,6 +73,69 @@ class HotPath:
             img.backward(dL_dimage)
         return out
 
+    # ------------------------------------------------------------------------------------------------ CUDA graph
+    def step_grads(self, view: int, dL_dimage: Tensor):
+        """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
+        nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
+        (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
+        form is cheaper on the host and can be captured into a CUDA graph."""
+        from . import diff_gaussian_rasterization as DGR
+        from .fk_lbs import (assemble_backward_raw, assemble_forward_raw, fk_lbs_backward_raw, fk_lbs_forward_raw)
+        with torch.no_grad():
+            p = self.params
+            W = self.mode == 'W'
+            (d_xyz, d_rot, d_scale, sk_T, weights, indices), c1 = fk_lbs_forward_raw(
+                p['xyz'], p['joints'], p['sk_r'], p['sk_d_rot'], p['sk_d_scale'], p['g_tr'], self.parents, self.root,
+                K=self.K, mode=self.mode, sp_W=p['sp_W'] if W else None, sp_radius=None if W else self.sp_radius,
+                sp_weight=self.sp_weight if self.mode == 'weighted_kernel' else None)
+            (points, scales, rotations, opacity), c2 = assemble_forward_raw(p['xyz'], p['scaling'], p['rotation'],
+                                                                            p['opacity'], d_xyz, d_rot, d_scale)
+            sh = torch.cat((p['f_dc'], p['f_rest']), dim=1)
+            color, depth, alpha, radii, st = DGR.rasterize_forward(self.settings[view], points, opacity, shs=sh,
+                                                                   scales=scales, rotations=rotations, quat_wxyz=False)
+            g = DGR.rasterize_backward(st, dL_dimage)
+            dxyz, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
+                c2, g['means3D'], g['scales'], g['rotations'], g['opacities'])
+            d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight = fk_lbs_backward_raw(
+                c1, dd_xyz, dd_rot, dd_scale)
+        grads = {'xyz': dxyz, 'scaling': dscaling, 'rotation': drotation, 'opacity': dopacity,
+                 'f_dc': g['shs'][:, :1], 'f_rest': g['shs'][:, 1:], 'sp_W': d_sp_W, 'joints': d_joints, 'sk_r': d_sk_r,
+                 'sk_d_rot': d_sk_d_rot, 'sk_d_scale': d_sk_d_scale, 'g_tr': d_g_tr, 'viewspace_points': g['means2D'],
+                 'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight}
+        out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
+               'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, p['sk_d_rot'], p['sk_d_scale'], p['g_tr'],
+                                                 weights, indices)}
+        return out, grads
+
+    def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3):
+        """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
+        the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
+        in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
+        from . import _lib
+        from . import diff_gaussian_rasterization as DGR
+        self.step_grads(view, dL_dimage)
+        torch.cuda.synchronize(self.device)
+        R = int(DGR.last_header_words(self.device)[0])
+        DGR.set_fixed_capacity(int(R * headroom) + 4096)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step_grads(view, dL_dimage)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            out, grads = self.step_grads(view, dL_dimage)
+        self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
+        torch.cuda.synchronize(self.device)
+        return graph, out, grads
+
+    def overflowed(self) -> bool:
+        from . import diff_gaussian_rasterization as DGR
+        return bool(DGR.last_header_words(self.device)[3] != 0)
+
     def zero_grad(self):
         for t in list(self.params.values()) + [self.sp_radius, self.sp_weight]:
             t.grad = None
