@@ -140,59 +140,56 @@ def run_ours(args, world, rank, local):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     params = list(hp.params.values())
 
-    def allreduce_grads(out):
+    from sk_gs_b200.dist import GradArena, allreduce_max_
+    arena = None
+    if world > 1:
+        shapes = {n: tuple(t.shape) for n, t in hp.params.items()}
+        shapes['viewspace_points'] = (cfg.P, 3)
+        arena = GradArena(shapes, dev)
+
+    def exchange(out, grads):
+        """The one exchange step of a data-parallel iteration: SUM of all gradients (mean over views), MAX of radii."""
         if world == 1:
             return
-        flat = torch.cat([p.grad.reshape(-1) for p in params] + [out['viewspace_points'].grad.reshape(-1)])
-        flat.mul_(1.0 / world)
-        dist.all_reduce(flat)
-        dist.all_reduce(out['radii'], op=dist.ReduceOp.MAX)
+        arena.pack(grads)
+        arena.allreduce(scale=1.0 / world, chunks=2)
+        allreduce_max_(out['radii'])
+
+    def upload():
+        for n, t in joint_host.items():
+            hp.params[n].data.copy_(t, non_blocking=True)
+        rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
+        rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
+        rs.campos.copy_(cam_host['campos'], non_blocking=True)
+        dL_dev.copy_(dL_host, non_blocking=True)
+
+    def download(img):
+        result_host.copy_((img.detach() * dL_dev).sum().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if args.graph and hp.overflowed():
+            raise RuntimeError('binning capacity of the captured graph exceeded')
+        return float(result_host[0])
 
     graph_state = {}
 
     def step(e2e: bool):
-        if args.graph and world == 1:
-            return step_graph(e2e)
-        hp.zero_grad()
         if e2e:
-            for n, t in joint_host.items():
-                hp.params[n].data.copy_(t, non_blocking=True)
-            rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
-            rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
-            rs.campos.copy_(cam_host['campos'], non_blocking=True)
-            dL = dL_dev
-            dL.copy_(dL_host, non_blocking=True)
+            upload()
+        if args.graph:
+            if 'g' not in graph_state:
+                graph_state['g'], graph_state['out'], graph_state['grads'] = hp.capture_step(view, dL_dev)
+            graph_state['g'].replay()
+            out, grads = graph_state['out'], graph_state['grads']
+        elif args.autograd:  # the drop-in autograd API (render_gs_offical + fk_lbs + assemble Functions)
+            hp.zero_grad()
+            out = hp.render(view)
+            out['images'].backward(dL_dev)
+            grads = dict(hp.grads())
+            grads['viewspace_points'] = out['viewspace_points'].grad
         else:
-            dL = dL_dev
-        out = hp.render(view)
-        img = out['images']
-        img.backward(dL)
-        allreduce_grads(out)
-        if e2e:
-            result_host.copy_((img.detach() * dL).sum().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return float(result_host[0])
-        return None
-
-    def step_graph(e2e: bool):
-        if 'g' not in graph_state:
-            graph_state['g'], graph_state['out'], graph_state['grads'] = hp.capture_step(view, dL_dev)
-        if e2e:
-            for n, t in joint_host.items():
-                hp.params[n].data.copy_(t, non_blocking=True)
-            rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
-            rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
-            rs.campos.copy_(cam_host['campos'], non_blocking=True)
-            dL_dev.copy_(dL_host, non_blocking=True)
-        graph_state['g'].replay()
-        if e2e:
-            img = graph_state['out']['images']
-            result_host.copy_((img.detach() * dL_dev).sum().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            if hp.overflowed():
-                raise RuntimeError('binning capacity of the captured graph exceeded')
-            return float(result_host[0])
-        return None
+            out, grads = hp.step_grads(view, dL_dev)
+        exchange(out, grads)
+        return download(out['images']) if e2e else None
 
     def timed(e2e: bool, K: int, Wu: int):
         for _ in range(Wu):
@@ -215,7 +212,7 @@ def run_ours(args, world, rank, local):
             dist.barrier()
         torch.cuda.synchronize()
         launches = _lib.launch_count() - launches0
-        if args.graph and world == 1:
+        if args.graph:
             launches = K * getattr(hp, 'launches_per_step', 0)  # replays do not pass through the launch counter
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -276,8 +273,8 @@ def run_ours(args, world, rank, local):
                                f'K=5 LBS mode W, fwd+bwd', 'num_rendered': R, 'views_per_step': world,
                    'parallelism': f'view-sharded dp{world}' + (' + NCCL grad allreduce' if world > 1 else ''),
                    'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs',
-                   'launch': 'CUDA graph replay (fixed binning capacity, overflow flag checked)' if (args.graph and world == 1)
-                   else 'eager launches'},
+                   'launch': 'CUDA graph replay (fixed binning capacity, overflow flag checked)' if args.graph
+                   else ('eager launches through the autograd API' if args.autograd else 'eager launches')},
         'clocks': clocks,
         'e2e': {'value': round(world * K / (ms_e2e * 1e-3), 2), 'unit': 'steps/s',
                 'ms_per_step': round(ms_e2e / K, 4),
@@ -436,6 +433,7 @@ def main():
     ap.add_argument('--ref-device', default='auto', choices=['auto', 'cpu', 'cuda'])
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--autograd', action='store_true', help='with --no-graph: time the drop-in autograd API path')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='launch every step eagerly instead of replaying a captured CUDA graph')
     args = ap.parse_args()

@@ -74,6 +74,12 @@ def lib():
         L.orc_preprocess_bwd.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, vp, u8p, vp, vp, C.c_int, C.c_float,
                                          f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p,
                                          f32p, vp, f32p, f32p, vp, vp, vp]
+        L.orc_sh_to_rgb.restype = None
+        L.orc_sh_to_rgb.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, u8p]
+        L.orc_cov3d.restype = None
+        L.orc_cov3d.argtypes = [C.c_int, f32p, C.c_float, f32p, C.c_int, f32p]
+        L.orc_cov2d.restype = None
+        L.orc_cov2d.argtypes = [C.c_int, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, C.c_float, f32p]
         _lib = L
     return _lib
 
@@ -90,6 +96,30 @@ def orc_exp(x: np.ndarray) -> np.ndarray:
     L = lib()
     x = np.asarray(x, np.float32)
     return np.array([L.orc_exp_scalar(float(v)) for v in x.ravel()], np.float32).reshape(x.shape)
+
+
+def sh_to_rgb(deg, shs, dirs):
+    """shs [n, M, 3], dirs [n, 3] (not necessarily unit) -> (rgb [n,3] = max(SH + 0.5, 0), clamped [n,3])."""
+    shs, dirs = f32(shs), f32(dirs)
+    n, M = shs.shape[0], shs.shape[1]
+    rgb, cl = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.uint8)
+    lib().orc_sh_to_rgb(n, int(deg), M, shs, dirs, rgb, cl)
+    return rgb, cl
+
+
+def cov3d(scales, rots, mod=1.0, quat_wxyz=False):
+    scales, rots = f32(scales), f32(rots)
+    out = np.zeros((scales.shape[0], 6), np.float32)
+    lib().orc_cov3d(scales.shape[0], scales, float(mod), rots, int(quat_wxyz), out)
+    return out
+
+
+def cov2d(means, cov6, viewmatrix, fx, fy, tanfovx, tanfovy):
+    means, cov6 = f32(means), f32(cov6)
+    out = np.zeros((means.shape[0], 3), np.float32)
+    lib().orc_cov2d(means.shape[0], means, cov6, f32(viewmatrix).reshape(-1), float(fx), float(fy), float(tanfovx),
+                    float(tanfovy), out)
+    return out
 
 
 def f32(a):

@@ -281,6 +281,32 @@ ORC_API ORC_HOT void orc_preprocess_fwd(int P, int D, int M, const float* means,
   }
 }
 
+/* ---- thin single-formula entry points (used by tests/test_oracle_golden.py against the reference's torch helpers) ---- */
+ORC_API void orc_sh_to_rgb(int n, int deg, int M, const float* shs, const float* dirs, float* rgb, uint8_t* clamped) {
+  for (int i = 0; i < n; i++)
+    sh_to_rgb(deg, shs + (size_t)i * M * 3, dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], rgb + 3 * i, clamped + 3 * i);
+}
+ORC_API void orc_cov3d(int n, const float* scales, float mod, const float* rots, int quat_wxyz, float* cov6) {
+  for (int i = 0; i < n; i++) cov3d_from_scale_rot(scales + 3 * i, mod, rots + 4 * i, quat_wxyz, cov6 + 6 * i);
+}
+/* cov2D = (J Rv) Sigma (J Rv)^T + 0.3 I, returns (c00, c01, c11) per point */
+ORC_API void orc_cov2d(int n, const float* means, const float* cov6, const float* V, float fx, float fy, float tanfovx,
+                       float tanfovy, float* out3) {
+  for (int i = 0; i < n; i++) {
+    const float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
+    const float pvx = V[0] * x + V[4] * y + V[8] * z + V[12];
+    const float pvy = V[1] * x + V[5] * y + V[9] * z + V[13];
+    const float pvz = V[2] * x + V[6] * y + V[10] * z + V[14];
+    float a0[3], a1[3], u0[3], u1[3], txc, tyc;
+    ewa_rows(pvx, pvy, pvz, fx, fy, tanfovx, tanfovy, V, a0, a1, &txc, &tyc);
+    sym3_mul(cov6 + 6 * i, a0, u0);
+    sym3_mul(cov6 + 6 * i, a1, u1);
+    out3[3 * i] = (a0[0] * u0[0] + a0[1] * u0[1] + a0[2] * u0[2]) + 0.3f;
+    out3[3 * i + 1] = a0[0] * u1[0] + a0[1] * u1[1] + a0[2] * u1[2];
+    out3[3 * i + 2] = (a1[0] * u1[0] + a1[1] * u1[1] + a1[2] * u1[2]) + 0.3f;
+  }
+}
+
 /* inclusive scan of tiles_touched; returns R.  reference gaussian_rasterizer_forward.cu:203-209 */
 ORC_API uint64_t orc_scan(int P, const uint32_t* tiles_touched, uint32_t* offsets) {
   uint64_t s = 0;

@@ -1,0 +1,89 @@
+"""View-sharded data parallelism for the hot path.
+
+Views (or reposing poses) of a step are independent given replicated parameters - the reference loops over them
+serially (/root/reference/networks/sk_gs.py:1220) and sums their densification statistics
+(networks/gaussian_splatting.py:509-512).  Here V views are split over the ranks of one NVLink/NVSwitch box, every rank
+runs the whole hot path for its views, and there is exactly ONE exchange step per training iteration: an all-reduce
+(SUM) of the Gaussian + skeleton gradients laid out in one flat fp32 arena, plus an all-reduce (MAX) of the screen radii
+(max-radius tracking, networks/sk_gs.py:1992-1996).  Forward-only rendering needs no collective at all.
+
+Plumbing is torch.distributed (NCCL on GPUs, gloo in the CPU tests); nothing here launches a kernel of its own.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_views(num_views: int, world: int, rank: int) -> List[int]:
+    """Contiguous block partition of range(num_views); the first (num_views % world) ranks get one extra view."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f'bad rank/world {rank}/{world}')
+    base, extra = divmod(num_views, world)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+class GradArena:
+    """One flat fp32 buffer holding every gradient that has to be summed over ranks.
+
+    Layout: the (large) per-Gaussian blocks first - SH gradients are 81 % of the bytes and are final right after
+    preprocess-backward, so `allreduce(chunks=...)` can reduce them while the LBS / FK backward of the same step is
+    still running on the compute stream - then the per-joint blocks, then the screen-space statistic."""
+
+    def __init__(self, shapes: Dict[str, Sequence[int]], device, order: Optional[Sequence[str]] = None):
+        self.names = list(order) if order is not None else sorted(shapes, key=lambda n: -int(torch.Size(shapes[n]).numel()))
+        self.shapes = {n: torch.Size(shapes[n]) for n in self.names}
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        o = 0
+        for n in self.names:
+            k = self.shapes[n].numel()
+            self.offsets[n] = (o, o + k)
+            o += k
+        self.flat = torch.zeros(o, dtype=torch.float32, device=device)
+
+    def view(self, name: str) -> Tensor:
+        a, b = self.offsets[name]
+        return self.flat[a:b].view(self.shapes[name])
+
+    def pack(self, grads: Dict[str, Optional[Tensor]], accumulate: bool = False):
+        """Copy (or add, for several views per rank) the gradients into the arena; missing / None entries count as 0."""
+        for n in self.names:
+            g = grads.get(n)
+            v = self.view(n)
+            if g is None:
+                if not accumulate:
+                    v.zero_()
+            elif accumulate:
+                v.add_(g.reshape(v.shape))
+            else:
+                v.copy_(g.reshape(v.shape))
+
+    def allreduce(self, scale: float = 1.0, group=None, chunks: int = 1, async_op: bool = False):
+        """SUM over ranks (after multiplying by `scale`, e.g. 1/V for a mean over views).  With chunks > 1 the arena is
+        reduced in that many contiguous pieces so that NCCL can start on the first piece early."""
+        if scale != 1.0:
+            self.flat.mul_(scale)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        n = self.flat.numel()
+        step = (n + chunks - 1) // max(chunks, 1)
+        works = []
+        for a in range(0, n, max(step, 1)):
+            w = dist.all_reduce(self.flat[a:a + step], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if async_op:
+                works.append(w)
+        return works
+
+    def unpack(self) -> Dict[str, Tensor]:
+        return {n: self.view(n) for n in self.names}
+
+
+def allreduce_max_(t: Tensor, group=None) -> Tensor:
+    """In-place MAX over ranks (screen radii)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t

@@ -1,0 +1,137 @@
+"""Generate golden vectors from the REFERENCE's own pure-torch helpers (run in the authoring container, where
+/root/reference exists; the .npz files are committed, the GPU box never needs the reference).
+
+The reference cannot be imported as-is (lietorch / pytorch3d / diff_gaussian_rasterization ... are absent):
+missing third-party packages are replaced by inert stub modules so that the modules holding the pure-torch formulas can
+be imported UNMODIFIED from /root/reference.  Functions exercised (all torch, CPU):
+  networks/encoders/sphere_harmonics.py : eval_sh, RGB2SH                       -> sh.npz
+  networks/GS_utils.py                   : build_rotation, compute_cov2D        -> cov.npz  (cov3D via R S S R^T as
+                                           build_covariance_from_scaling_rotation :44-82, whose "cuda" literal is bypassed)
+  my_ext/ops_3d/rigid.py                 : quaternion_to_Rt                     -> fk.npz
+  networks/sk_gs.py                      : find_root, skeleton_warp, skeleton_warp_v0   -> fk.npz
+  my_ext/ops_3d/coord_trans_opencv.py    : perspective                          -> cam.npz
+"""
+import importlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get('REF', '/root/reference')
+OUT = os.path.dirname(os.path.abspath(__file__))
+STUBS = ['lietorch', 'pytorch3d', 'pykdtree', 'plyfile', 'torchmetrics', 'dearpygui', 'imageio', 'matplotlib', 'cv2',
+         'diff_gaussian_rasterization', 'open3d', 'trimesh', 'lpips', 'skimage', 'PIL', 'tqdm_joblib', 'kornia',
+         'tensorboard', 'tensorboardX', 'pymeshlab', 'xatlas', 'nvdiffrast', 'tinycudann', 'seaborn', 'termcolor',
+         'prettytable', 'torch_scatter', 'einops_exts', 'pyrender', 'mcubes', 'pysdf', 'OpenGL', 'glfw', 'moderngl']
+
+
+class _Anything(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        return _Dummy()
+
+
+class _Dummy:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]  # used as a bare decorator
+        return _Dummy()
+
+    def __getattr__(self, name):
+        return _Dummy()
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+    def __iter__(self):
+        return iter(())
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split('.')[0] in STUBS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _Anything(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def main():
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REF)
+    os.chdir(REF)
+    g = torch.Generator().manual_seed(20241017)
+    # ---- SH
+    sh_mod = importlib.import_module('networks.encoders.sphere_harmonics')
+    P = 257
+    sh = torch.randn(P, 3, 16, generator=g) * 0.3
+    dirs = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
+    sh_out = {f'rgb_deg{d}': sh_mod.eval_sh(d, sh, dirs).numpy() for d in range(4)}
+    rgb = torch.rand(P, 3, generator=g)
+    np.savez(os.path.join(OUT, 'sh.npz'), sh=sh.numpy(), dirs=dirs.numpy(), rgb=rgb.numpy(),
+             rgb2sh=sh_mod.RGB2SH(rgb).numpy(), **sh_out)
+    # ---- covariances
+    gs = importlib.import_module('networks.GS_utils')
+    q = torch.randn(P, 4, generator=g)
+    s = torch.exp(torch.randn(P, 3, generator=g) * 0.5 - 3.0)
+    R = gs.build_rotation(q)  # normalises q, xyzw
+    L = R @ torch.diag_embed(s)
+    cov = L @ L.transpose(1, 2)
+    cov6 = torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], -1)
+    pts = torch.randn(P, 3, generator=g) * 0.5
+    Tw2v = torch.eye(4)
+    ang = 0.3
+    Tw2v[:3, :3] = torch.tensor([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    Tw2v[:3, 3] = torch.tensor([0.1, -0.2, 4.0])
+    fx, fy, tx, ty = 1100.0, 1050.0, 0.36, 0.30
+    cov2d = gs.compute_cov2D(pts, cov6, Tw2v, fx, fy, tx, ty)
+    np.savez(os.path.join(OUT, 'cov.npz'), q=q.numpy(), s=s.numpy(), R=R.numpy(), cov6=cov6.numpy(), pts=pts.numpy(),
+             Tw2v=Tw2v.numpy(), fx=fx, fy=fy, tanfovx=tx, tanfovy=ty, cov2d=cov2d.numpy())
+    # ---- FK: matrix formulation of the reference + its tree builder
+    rigid = importlib.import_module('my_ext.ops_3d.rigid')
+    sk = importlib.import_module('networks.sk_gs')
+    fk = {}
+    for idx, M in enumerate((3, 8, 24, 33, 64)):
+        if idx == 3:
+            father = torch.tensor([-1] + list(range(M - 1)))  # chain
+        else:
+            father = torch.tensor([-1] + [int(torch.randint(0, j, (1,), generator=g)) for j in range(1, M)])
+        parents, depth, root = sk.find_root(father)
+        joints = torch.randn(M, 3, generator=g).double() * 0.4
+        r = torch.nn.functional.normalize(torch.randn(M, 4, generator=g).double(), dim=-1)
+        gq = torch.nn.functional.normalize(torch.randn(4, generator=g).double(), dim=-1)
+        gt = torch.randn(3, generator=g).double() * 0.1
+        Rm = rigid.quaternion_to_Rt(r)  # [M,4,4] rotation only
+        local = Rm.clone()
+        local[:, :3, 3] = joints - (Rm[:, :3, :3] @ joints[:, :, None])[:, :, 0]  # rotation about the joint position
+        G = rigid.quaternion_to_Rt(gq, gt)
+        T_jump = sk.skeleton_warp(local, G, parents, root)
+        T_v0 = sk.skeleton_warp_v0(local, G, parents, root)
+        fk.update({f'father{idx}': father.numpy(), f'parents{idx}': parents.numpy(), f'depth{idx}': depth.numpy(),
+                   f'root{idx}': np.int64(root), f'joints{idx}': joints.numpy(), f'r{idx}': r.numpy(),
+                   f'g_tr{idx}': torch.cat([gt, gq]).numpy(), f'T_jump{idx}': T_jump.numpy(), f'T_v0{idx}': T_v0.numpy()})
+    np.savez(os.path.join(OUT, 'fk.npz'), n=np.int64(5), **fk)
+    # ---- camera
+    cv = importlib.import_module('my_ext.ops_3d.coord_trans_opencv')
+    Tv2c = cv.perspective(fovy=0.6911, n=0.01, f=1000.0, size=(800, 800))
+    Tv2c2 = cv.perspective(fovy=0.5, n=0.01, f=1000.0, size=(1920, 1080))
+    np.savez(os.path.join(OUT, 'cam.npz'), Tv2c_800=Tv2c.numpy(), Tv2c_1080p=Tv2c2.numpy())
+    print('golden vectors written to', OUT)
+
+
+if __name__ == '__main__':
+    main()

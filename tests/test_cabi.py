@@ -1,0 +1,97 @@
+"""C ABI of libskgs_b200.so without a GPU: the library loads, exports every symbol include/skgs_b200.h declares, the
+host-only entry points work and argument errors are reported the way the header promises."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from sk_gs_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, 'include', 'skgs_b200.h')) as f:
+        src = f.read()
+    return sorted(set(re.findall(r'SKGS_API\s+[\w\s\*]+?\b(skgs_\w+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f'{name} declared in include/skgs_b200.h but not exported'
+    assert sorted(_lib.check_exports()) == declared  # the ctypes binding covers exactly the header
+    assert L.skgs_abi_version() == 1 and L.skgs_built_for_sm() == 100
+
+
+def test_built_for_sm100a_only():
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+
+
+def test_layout_query_is_host_only_and_consistent():
+    L = _lib.lib()
+    lay = _lib.RasterLayout()
+    assert L.skgs_raster_layout_query(100000, 800, 800, 1000000, C.byref(lay)) == 0
+    offs = {n: getattr(lay, n) for n in _lib._LAYOUT_FIELDS}
+    assert all(v % 256 == 0 for k, v in offs.items())
+    assert offs['header'] == 0 and offs['scan_state'] > 0 and offs['means2D'] > offs['scan_state']
+    assert lay.geom_bytes >= 100000 * (8 + 4 + 24 + 16 + 16 + 1 + 4 + 4 + 48)
+    assert lay.binning_bytes >= 1000000 * 24
+    assert lay.img_bytes >= 2500 * 8 + 2 * 800 * 800 * 4
+    # 800x800 -> 2500 tiles -> 12 tile bits -> 6 radix passes (even): the sorted lists end in the emission buffers
+    assert offs['keys_sorted'] == offs['keys_unsorted'] and offs['point_list'] == offs['vals_unsorted']
+    # 400x400 -> 625 tiles -> 10 bits -> 6 passes; 160x96 -> 60 tiles -> 6 bits -> 5 passes (odd): separate buffers
+    assert L.skgs_raster_layout_query(10, 160, 96, 1000, C.byref(lay)) == 0
+    assert lay.keys_sorted != lay.keys_unsorted and lay.point_list != lay.vals_unsorted
+
+
+def test_errors_are_reported_not_swallowed():
+    L = _lib.lib()
+    lay = _lib.RasterLayout()
+    assert L.skgs_raster_layout_query(-1, 800, 800, 0, C.byref(lay)) == -1
+    assert b'bad sizes' in L.skgs_last_error()
+    assert L.skgs_raster_layout_query(10, 800, 800, 1 << 27, C.byref(lay)) == -1
+    assert b'2^27' in L.skgs_last_error()
+    # NULL settings / skeleton are rejected before any CUDA call
+    assert L.skgs_raster_forward_geometry(None, 0, 0, *([None] * 11)) == -1
+    assert b'settings is NULL' in L.skgs_last_error()
+    assert L.skgs_fk_lbs_forward(None, 0, *([None] * 8)) == -1
+    sk = _lib.Skeleton(M=2000, L=1, root=0, K=5, mode=0, temperature=1.0)
+    assert L.skgs_fk_lbs_forward(C.byref(sk), 0, *([None] * 8)) == -1
+    assert b'M=2000' in L.skgs_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(-1, 'demo')
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under sk_gs_b200/ may import, link or call it."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'sk_gs_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                with open(os.path.join(dirpath, fn)) as f:
+                    txt = f.read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', txt, re.M) or 'liboracle' in txt or '#include "../../oracle' in txt:
+                    bad.append(fn)
+    assert not bad, bad
+
+
+def test_cpu_tensors_fail_loudly():
+    import torch
+    from sk_gs_b200 import diff_gaussian_rasterization as DGR
+    from sk_gs_b200.fk_lbs import fk_lbs
+    from sk_gs_b200.pipeline import raster_settings_for
+    from sk_gs_b200 import scene as S
+    sc = S.make_scene('c1', P=8)
+    rs = raster_settings_for(sc.cameras[0], 'cpu')
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        DGR.rasterize_forward(rs, sc.xyz, torch.sigmoid(sc.opacity), shs=torch.cat((sc.f_dc, sc.f_rest), 1),
+                              scales=sc.scaling.exp(), rotations=sc.rotation)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        fk_lbs(sc.xyz, sc.joints, sc.sk_r, sc.sk_d_rot, sc.sk_d_scale, sc.g_tr, sc.parents, sc.root, sp_W=sc.sp_W)
