@@ -74,7 +74,8 @@ typedef struct skgs_raster_settings {
   int32_t sh_degree;        /* active degree D, 0..3 */
   int32_t quat_wxyz;        /* 1: rotations are (w,x,y,z) (upstream boundary B1); 0: (x,y,z,w) (in-tree boundary B2) */
   int32_t prefiltered;      /* accepted for API parity; culled points are simply skipped */
-  int32_t debug;            /* accepted for API parity */
+  int32_t debug;            /* bit 0: accepted for API parity; bit 1: stop after binning (tests);
+                               bit 3: use the experimental tile-bucketed binning instead of duplicate + onesweep */
   const float* viewmatrix;  /* device [16] */
   const float* projmatrix;  /* device [16] */
   const float* campos;      /* device [3] */
@@ -96,6 +97,8 @@ typedef struct skgs_raster_layout {
   size_t tiles_touched;  /* uint32 [P] */
   size_t point_offsets;  /* uint32 [P]   inclusive prefix sum of tiles_touched */
   size_t scan_state;     /* uint64 [ceil(P/256)+1] look-back words of the fused scan */
+  size_t tile_count;     /* uint32 [tiles]  list length of every tile (counted in preprocess, bucketed binning) */
+  size_t tile_cursor;    /* uint32 [tiles]  running write cursor of every tile's bucket */
   size_t geom_grads;     /* float  [P][12] packed backward accumulators: mean2D.xy conic.abc opacity depth - rgb - */
   /* binning (capacity R_cap entries) */
   size_t keys_unsorted;  /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */

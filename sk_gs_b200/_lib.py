@@ -24,7 +24,8 @@ class RasterSettings(C.Structure):
 
 
 _LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
-                  'rgbd', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads', 'keys_unsorted',
+                  'rgbd', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'tile_count', 'tile_cursor', 'geom_grads',
+                  'keys_unsorted',
                   'vals_unsorted', 'keys_sorted', 'point_list', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
                   'final_T', 'tile_order', 'work_counters']
 

@@ -167,6 +167,11 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   // ---- geom (header + scan_state first: they are reset by one memset per forward)
   out->header = take(sizeof(skgs_raster_header));
   out->scan_state = take(((Pz + 255) / 256 + 1) * sizeof(uint64_t));
+  {
+    const size_t ntiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    out->tile_count = take(ntiles * 4);   // zeroed together with header + scan_state
+    out->tile_cursor = take(ntiles * 4);
+  }
   out->means2D = take(Pz * 8);
   out->depths = take(Pz * 4);
   out->cov3D = take(Pz * 24);
@@ -236,7 +241,7 @@ int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32
   rc = skgs_raster_layout_query(P, rp.W, rp.H, 0, &lay);
   if (rc) return rc;
   return launch_preprocess_scan(rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                (char*)geom, lay, radii, num_rendered_host, (cudaStream_t)stream);
+                                (char*)geom, lay, radii, num_rendered_host, (s->debug & 8) != 0, (cudaStream_t)stream);
 }
 
 int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning, int64_t R_cap,
@@ -255,11 +260,16 @@ int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* g
   // reset the overflow flag and the sort tickets (the render stage may be re-run on the same geometry)
   auto* hdr = reinterpret_cast<skgs_raster_header*>((char*)geom + lay.header);
   SKGS_CUDA(cudaMemsetAsync(&hdr->overflow, 0, sizeof(uint32_t) * 9, st));
-  rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, phys, radii, R_cap, R_hint, num_rendered_host, st);
+  if (!(s->debug & 8)) {  // default: duplicate-with-keys + onesweep radix sort (the algorithm named in the spec)
+    rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, phys, radii, R_cap, R_hint, num_rendered_host, st);
+    if (rc) return rc;
+    rc = launch_tile_order(rp, (char*)img, lay, st);
+  } else {                // experimental: tile-bucketed binning (binning_bucket.cu), bit-identical output
+    rc = launch_binning_bucket(rp, (char*)geom, (char*)binning, (char*)img, lay, phys, radii, R_cap, true,
+                               num_rendered_host, st);
+  }
   if (rc) return rc;
   if (s->debug & 2) return SKGS_OK;  // test hook: stop after binning
-  rc = launch_tile_order(rp, (char*)img, lay, st);
-  if (rc) return rc;
   return launch_composite_fwd(rp, (char*)geom, (char*)binning, (char*)img, lay, out_color, out_depth, out_alpha, st);
 }
 

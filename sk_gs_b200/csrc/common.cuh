@@ -137,9 +137,12 @@ struct RasterParams {
 int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                            const float* opacities, const float* scales, const float* rotations,
                            const float* cov3D_precomp, char* geom, const skgs_raster_layout& lay, int32_t* radii,
-                           uint32_t* num_rendered_host, cudaStream_t st);
+                           uint32_t* num_rendered_host, bool count_tiles, cudaStream_t st);
 int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                    const int32_t* radii, int64_t R_cap, int64_t R_hint, uint32_t* num_rendered_host, cudaStream_t st);
+int launch_binning_bucket(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
+                          const skgs_raster_layout& phys, const int32_t* radii, int64_t R_cap, bool write_keys,
+                          uint32_t* num_rendered_host, cudaStream_t st);
 int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st);
 int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                          float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);

@@ -55,12 +55,22 @@ tile_order_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restr
     atomicAdd(&s_hist[length_bin(r.y - r.x)], 1u);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // descending: the largest bin first
-    uint32_t run = 0;
-    for (int b = TO_BINS - 1; b >= 0; b--) {
-      s_base[b] = run;
-      run += s_hist[b];
+  // descending exclusive prefix (largest bin first): block scan over the reversed histogram
+  {
+    __shared__ uint32_t s_wsum[TO_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = tid < TO_BINS ? s_hist[TO_BINS - 1 - tid] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_wsum[w];
+    if (tid < TO_BINS) s_base[TO_BINS - 1 - tid] = woff + incl - v;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < tiles; t += TO_THREADS) {
@@ -141,6 +151,7 @@ __device__ __forceinline__ bool footprint_may_hit(const float4 g0, const float4 
 // forward.  Work item = 8 x 4 pixels (one pixel per lane), 8 items per tile.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ITEM_W = 8, ITEM_H = 4, ITEMS_PER_TILE = (TILE / ITEM_W) * (TILE / ITEM_H);
+constexpr int RSLOTS = 6, RVALS = 10, RSTRIDE = 33;  // backward reduction staging (see composite_bwd_kernel)
 
 __global__ void __launch_bounds__(CW_THREADS)
 composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
@@ -257,8 +268,36 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// backward.  Same work items; lane j keeps the warp-reduced gradients of batch entry j.
+// backward.  Same work items as the forward.
 // ------------------------------------------------------------------------------------------------------------------
+// Sum the parked rows (two per lane), leave each row total in the row's pad word, then lane s < n flushes slot s with
+// three 16-byte vector REDs: one RED set per (item, Gaussian).
+__device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id, int n, int lane, float ddelx_dx,
+                                            float ddely_dy, float* __restrict__ ggrad) {
+  __syncwarp();
+  for (int r = lane; r < n * RVALS; r += 32) {
+    const float* row = part + r * RSTRIDE;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+      s0 += row[k]; s1 += row[k + 1]; s2 += row[k + 2]; s3 += row[k + 3];
+    }
+    part[r * RSTRIDE + 32] = (s0 + s1) + (s2 + s3);
+  }
+  __syncwarp();
+  if (lane < n) {
+    const float* t = part + lane * (RVALS * RSTRIDE) + 32;
+    const float mx = t[0 * RSTRIDE], my = t[1 * RSTRIDE], ca = t[2 * RSTRIDE], cb = t[3 * RSTRIDE];
+    const float cc = t[4 * RSTRIDE], op = t[5 * RSTRIDE], z = t[6 * RSTRIDE];
+    const float r = t[7 * RSTRIDE], g = t[8 * RSTRIDE], b = t[9 * RSTRIDE];
+    float* dst = ggrad + (size_t)slot_id[lane] * NGRAD;
+    red_add_v4(dst, mx * ddelx_dx, my * ddely_dy, -0.5f * ca, -0.5f * cb);
+    red_add_v4(dst + 4, -0.5f * cc, op, z, 0.f);
+    red_add_v4(dst + 8, r, g, b, 0.f);
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(CW_THREADS)
 composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
                      uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
@@ -271,10 +310,17 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
   __shared__ float4 s_g0[CW_WARPS][32];
   __shared__ float4 s_g1[CW_WARPS][32];
   __shared__ float4 s_c[CW_WARPS][32];
+  // cross-lane reduction through shared memory: every lane parks its 10 partial sums of up to RSLOTS surviving
+  // Gaussians (rows of 32 + 1 pad word, conflict free), then the 10*RSLOTS rows are summed two per lane - about 35
+  // instructions per surviving Gaussian instead of 100 for ten 5-step shuffle reductions
+  __shared__ float s_part[CW_WARPS][RSLOTS * RVALS * RSTRIDE];
+  __shared__ uint32_t s_slot_id[CW_WARPS][RSLOTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* g0s = s_g0[warp];
   float4* g1s = s_g1[warp];
   float4* cs = s_c[warp];
+  float* part = s_part[warp];
+  uint32_t* slot_id = s_slot_id[warp];
   const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
   const size_t HW = (size_t)H * W;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
@@ -310,6 +356,7 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
     // positions >= mymax contribute to no pixel of this item: start there and walk to the front
+    int nslots = 0;
     uint32_t id_nxt = 0;
     Staged nxt;
     if ((int)mymax - 1 - lane >= 0) gather(point_list, means2D, conic_opacity, rgbd, range.x + mymax - 1 - lane, nxt);
@@ -321,8 +368,6 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
       if (top - 33 - lane >= 0) gather_id(id_nxt, means2D, conic_opacity, rgbd, nxt);
       if (top - 65 - lane >= 0) id_nxt = __ldg(point_list + range.x + top - 65 - lane);
       const int nb = min(32, top);
-      float t_mx = 0.f, t_my = 0.f, t_ca = 0.f, t_cb = 0.f, t_cc = 0.f, t_op = 0.f, t_r = 0.f, t_g = 0.f, t_b = 0.f,
-            t_z = 0.f;
       const bool may = lane < nb && footprint_may_hit(g0s[lane], g1s[lane], fx0, fx0 + (float)(ITEM_W - 1), fy0,
                                                         fy0 + (float)(ITEM_H - 1));
       uint32_t todo = __ballot_sync(0xffffffffu, may);
@@ -349,7 +394,7 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
         if (valid) {
           const float4 c = cs[j];
           const float A = -2.0f * g0.z, B = -g0.w, Cc = -2.0f * g1.x, o = g1.y;
-          const float inv = __frcp_rn(1.0f - alpha);
+          const float inv = __fdividef(1.0f, 1.0f - alpha);
           T = T * inv;
           const float w = alpha * T;
           ac0 = fmaf(la, lc0 - ac0, ac0);
@@ -371,23 +416,24 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
           a_cc = gdy * dy * dL_dG;
           a_op = G * dL_dalpha;
         }
-        a_mx = warp_sum(a_mx); a_my = warp_sum(a_my); a_ca = warp_sum(a_ca); a_cb = warp_sum(a_cb);
-        a_cc = warp_sum(a_cc); a_op = warp_sum(a_op); a_r = warp_sum(a_r); a_g = warp_sum(a_g);
-        a_b = warp_sum(a_b); a_z = warp_sum(a_z);
-        if (lane == j) {
-          t_mx = a_mx; t_my = a_my; t_ca = a_ca; t_cb = a_cb; t_cc = a_cc; t_op = a_op; t_r = a_r; t_g = a_g;
-          t_b = a_b; t_z = a_z;
+        // park the partial sums of this Gaussian in slot `nslots`
+        {
+          float* row = part + nslots * (RVALS * RSTRIDE) + lane;
+          row[0 * RSTRIDE] = a_mx; row[1 * RSTRIDE] = a_my; row[2 * RSTRIDE] = a_ca; row[3 * RSTRIDE] = a_cb;
+          row[4 * RSTRIDE] = a_cc; row[5 * RSTRIDE] = a_op; row[6 * RSTRIDE] = a_z; row[7 * RSTRIDE] = a_r;
+          row[8 * RSTRIDE] = a_g; row[9 * RSTRIDE] = a_b;
+          if (lane == 0) slot_id[nslots] = __float_as_uint(g1.w);
+        }
+        nslots++;
+        if (nslots == RSLOTS) {
+          flush_slots(part, slot_id, nslots, lane, ddelx_dx, ddely_dy, ggrad);
+          nslots = 0;
         }
       }
-      // flush: lane j owns entry j of this batch
-      if (lane < nb) {
-        const uint32_t g = __float_as_uint(g1s[lane].w);
-        float* dst = ggrad + (size_t)g * NGRAD;
-        if (t_mx != 0.f || t_my != 0.f || t_ca != 0.f || t_cb != 0.f)
-          red_add_v4(dst, t_mx * ddelx_dx, t_my * ddely_dy, -0.5f * t_ca, -0.5f * t_cb);
-        if (t_cc != 0.f || t_op != 0.f || t_z != 0.f) red_add_v4(dst + 4, -0.5f * t_cc, t_op, t_z, 0.f);
-        if (t_r != 0.f || t_g != 0.f || t_b != 0.f) red_add_v4(dst + 8, t_r, t_g, t_b, 0.f);
-      }
+    }
+    if (nslots > 0) {
+      flush_slots(part, slot_id, nslots, lane, ddelx_dx, ddely_dy, ggrad);
+      nslots = 0;
     }
   }
 }

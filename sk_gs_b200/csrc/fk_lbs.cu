@@ -424,6 +424,233 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// LBS backward, joint-major variant (M <= 256).  The first version added 14 values per (Gaussian, joint) pair with
+// shared-memory atomics (66 us at P = 100K: the ATOMS pipe is the limit).  Here a CTA stages a chunk of 256 Gaussians
+// in shared memory (phase 1, thread = Gaussian: gradient w.r.t. the K weights, weight-function backward, dL/dsp_W rows
+// written coalesced), then re-maps its threads to (joint, slice) pairs (phase 2): each thread walks the Gaussians of its
+// slice, and accumulates the contributions to ITS joint in 19 registers that live across all chunks of the persistent
+// CTA.  No atomics until the final cross-slice / cross-CTA reduction.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JM_CHUNK = 256;
+constexpr int JM_MAX_M = 256;
+
+struct JmChunk {          // SoA records of one chunk
+  float p[JM_CHUNK][3];
+  float G[JM_CHUNK][3];
+  float gr[JM_CHUNK][4];
+  float gs[JM_CHUNK][3];
+  float w[JM_CHUNK][MAXK];
+  float dl[JM_CHUNK][MAXK];   // mode W: dL/dlogit_k ; other modes: dL/d(d2_k)
+  float e1[JM_CHUNK][MAXK];   // kernel modes: contribution to d/d(log radius) of joint idx_k
+  float e2[JM_CHUNK][MAXK];   // weighted_kernel: contribution to d/d(weight logit)
+  int idx[JM_CHUNK][MAXK];
+  uint16_t list[JM_CHUNK * MAXK];  // (g << 3 | k) pairs grouped by joint
+  uint32_t cnt[JM_MAX_M];          // pairs per joint in this chunk
+  uint32_t off[JM_MAX_M];
+};
+
+size_t lbs_bwd_jm_smem_bytes(int M) { return sizeof(JmChunk) + (size_t)M * (3 + 7 + 4 + 3 + 2 + 1 + NJ) * sizeof(float); }
+
+__global__ void __launch_bounds__(FK_THREADS)
+lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const float* __restrict__ sk_T,
+                  const float* __restrict__ weights, const int64_t* __restrict__ indices,
+                  const float* __restrict__ g_dxyz, const float* __restrict__ g_drot,
+                  const float* __restrict__ g_dscale, const float* __restrict__ g_w, float* __restrict__ dL_dsp_W,
+                  float* __restrict__ jacc /*[M][NJ]*/) {
+  extern __shared__ __align__(16) unsigned char jm_raw[];
+  JmChunk& C = *reinterpret_cast<JmChunk*>(jm_raw);
+  float* tab = reinterpret_cast<float*>(jm_raw + sizeof(JmChunk));
+  const int M = sk.M, K = sk.K;
+  float* s_pos = tab;             // [M][3]
+  float* s_T = s_pos + 3 * M;     // [M][7]
+  float* s_dq = s_T + 7 * M;      // [M][4]
+  float* s_ds = s_dq + 4 * M;     // [M][3]
+  float* s_aux = s_ds + 3 * M;    // [M][2]
+  float* s_sig = s_aux + 2 * M;   // [M]
+  float* s_acc = s_sig + M;       // [M][NJ]
+  const int tid = threadIdx.x;
+  for (int a = tid; a < M; a += blockDim.x) {
+    for (int c = 0; c < 3; c++) s_pos[3 * a + c] = sk.joints[3 * a + c];
+    for (int c = 0; c < 3; c++) s_T[7 * a + c] = sk_T[7 * a + c];
+    const Quat q = q_normalize(load_q(sk_T + 7 * a + 3));
+    s_T[7 * a + 3] = q.x; s_T[7 * a + 4] = q.y; s_T[7 * a + 5] = q.z; s_T[7 * a + 6] = q.w;
+    for (int c = 0; c < 4; c++) s_dq[4 * a + c] = sk.sk_d_rot[4 * a + c];
+    for (int c = 0; c < 3; c++) s_ds[3 * a + c] = sk.sk_d_scale[3 * a + c];
+    s_aux[2 * a] = s_aux[2 * a + 1] = 0.f;
+    s_sig[a] = 1.f;
+    if (sk.mode == SKGS_LBS_KERNEL || sk.mode == SKGS_LBS_WEIGHTED_KERNEL) {
+      const float r = expf(sk.sp_radius[a]);
+      s_aux[2 * a] = 1.0f / (2.0f * r * r);
+      s_aux[2 * a + 1] = 1.0f / (r * r);
+      if (sk.mode == SKGS_LBS_WEIGHTED_KERNEL) s_sig[a] = sigmoidf(sk.sp_weight[a]);
+    }
+  }
+  for (int k = tid; k < M * NJ; k += blockDim.x) s_acc[k] = 0.f;
+  __syncthreads();
+  // phase-2 role of this thread: joint `ja`, slice `js` of the chunk
+  const int Mp = ((M + 31) / 32) * 32;          // joints padded to whole warps
+  const int nslice = FK_THREADS / Mp;           // >= 1 because M <= 256
+  const int ja = tid % Mp, js = tid / Mp;
+  const bool jactive = ja < M && js < nslice;
+  Quat qa = {0.f, 0.f, 0.f, 1.f};
+  Vec3 pa = {0.f, 0.f, 0.f};
+  if (ja < M) {
+    qa = {s_T[7 * ja + 3], s_T[7 * ja + 4], s_T[7 * ja + 5], s_T[7 * ja + 6]};
+    pa = {s_pos[3 * ja], s_pos[3 * ja + 1], s_pos[3 * ja + 2]};
+  }
+  float acc[NJ];
+#pragma unroll
+  for (int c = 0; c < NJ; c++) acc[c] = 0.f;
+
+  for (int base = blockIdx.x * JM_CHUNK; base < P; base += gridDim.x * JM_CHUNK) {
+    const int n = min(JM_CHUNK, P - base);
+    for (int a = tid; a < M; a += blockDim.x) C.cnt[a] = 0;
+    __syncthreads();
+    // ---------------------------------------------------------------- phase 1: thread = Gaussian
+    uint32_t rank[MAXK];
+    int myidx[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; k++) { rank[k] = 0; myidx[k] = -1; }
+    if (tid < n) {
+      const int i = base + tid;
+      const Vec3 p = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+      const Vec3 G = g_dxyz ? Vec3{g_dxyz[3 * i], g_dxyz[3 * i + 1], g_dxyz[3 * i + 2]} : Vec3{0.f, 0.f, 0.f};
+      const float4 gr = g_drot ? *reinterpret_cast<const float4*>(g_drot + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const Vec3 gs = g_dscale ? Vec3{g_dscale[3 * i], g_dscale[3 * i + 1], g_dscale[3 * i + 2]} : Vec3{0.f, 0.f, 0.f};
+      C.p[tid][0] = p.x; C.p[tid][1] = p.y; C.p[tid][2] = p.z;
+      C.G[tid][0] = G.x; C.G[tid][1] = G.y; C.G[tid][2] = G.z;
+      C.gr[tid][0] = gr.x; C.gr[tid][1] = gr.y; C.gr[tid][2] = gr.z; C.gr[tid][3] = gr.w;
+      C.gs[tid][0] = gs.x; C.gs[tid][1] = gs.y; C.gs[tid][2] = gs.z;
+      float w[MAXK], dw[MAXK];
+      int idx[MAXK];
+      float wdw = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXK; k++)
+        if (k < K) {
+          w[k] = weights[(size_t)i * K + k];
+          const int a = idx[k] = (int)indices[(size_t)i * K + k];
+          const float* Ta = s_T + 7 * a;
+          const Vec3 y = q_rotate({Ta[3], Ta[4], Ta[5], Ta[6]}, p);
+          float d = G.x * (y.x + Ta[0]) + G.y * (y.y + Ta[1]) + G.z * (y.z + Ta[2]);
+          d += gr.x * s_dq[4 * a] + gr.y * s_dq[4 * a + 1] + gr.z * s_dq[4 * a + 2] + gr.w * s_dq[4 * a + 3];
+          d += gs.x * s_ds[3 * a] + gs.y * s_ds[3 * a + 1] + gs.z * s_ds[3 * a + 2];
+          if (g_w) d += g_w[(size_t)i * K + k];
+          dw[k] = d;
+          wdw += w[k] * d;
+          C.w[tid][k] = w[k];
+          C.idx[tid][k] = a;
+          myidx[k] = a;
+          rank[k] = atomicAdd(&C.cnt[a], 1u);
+        }
+      if (sk.mode == SKGS_LBS_W) {
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K) C.dl[tid][k] = w[k] * (dw[k] - wdw);
+      } else {
+        float d2[MAXK], e[MAXK];
+        float S = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K) {
+            const int a = idx[k];
+            const float dx = p.x - s_pos[3 * a], dy = p.y - s_pos[3 * a + 1], dz = p.z - s_pos[3 * a + 2];
+            d2[k] = dx * dx + dy * dy + dz * dz;
+            e[k] = sk.mode == SKGS_LBS_DIST ? 0.f : expf(-d2[k] * s_aux[2 * a]);
+            S += e[k] * s_sig[a] + 1e-7f;
+          }
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K) {
+            const int a = idx[k];
+            float dd2, r1 = 0.f, r2 = 0.f;
+            if (sk.mode == SKGS_LBS_DIST) {
+              dd2 = -(w[k] * (dw[k] - wdw)) / sk.temperature;
+            } else {
+              const float du = (dw[k] - wdw) / S;
+              dd2 = -du * s_sig[a] * e[k] * s_aux[2 * a];
+              r1 = du * s_sig[a] * e[k] * d2[k] * s_aux[2 * a + 1];
+              r2 = du * e[k] * s_sig[a] * (1.0f - s_sig[a]);
+            }
+            C.dl[tid][k] = dd2;
+            C.e1[tid][k] = r1;
+            C.e2[tid][k] = r2;
+          }
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- group the (Gaussian, k) pairs by joint
+    if (tid < 32) {  // exclusive scan of the per-joint counts by one warp (M <= 256: 8 per lane)
+      uint32_t run = 0;
+      for (int a0 = 0; a0 < M; a0 += 32) {
+        const int a = a0 + tid;
+        const uint32_t c = a < M ? C.cnt[a] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += t;
+        }
+        if (a < M) C.off[a] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < MAXK; k++)
+      if (myidx[k] >= 0) C.list[C.off[myidx[k]] + rank[k]] = (uint16_t)((tid << 3) | k);
+    __syncthreads();
+    // ---------------------------------------------------------------- dL/dsp_W rows of the chunk, coalesced
+    if (sk.mode == SKGS_LBS_W && dL_dsp_W != nullptr) {
+      float* out = dL_dsp_W + (size_t)base * M;
+      for (int e = tid; e < n * M; e += blockDim.x) {
+        const int g = e / M, a = e - g * M;
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K && C.idx[g][k] == a) v = C.dl[g][k];
+        out[e] = v;
+      }
+    }
+    // ---------------------------------------------------------------- phase 2: thread = (joint, slice)
+    if (jactive) {  // thread (ja, js) takes every nslice-th pair of joint ja's list: all lanes do useful work
+      const uint32_t beg = C.off[ja], cntj = C.cnt[ja];
+      for (uint32_t e = js; e < cntj; e += nslice) {
+        const uint32_t code = C.list[beg + e];
+        const int g = (int)(code >> 3), mk = (int)(code & 7u);
+        const float wk = C.w[g][mk];
+        const Vec3 p = {C.p[g][0], C.p[g][1], C.p[g][2]};
+        const Vec3 wG = {wk * C.G[g][0], wk * C.G[g][1], wk * C.G[g][2]};
+        const Quat gq = q_rotate_grad_q(qa, p, wG);
+        acc[0] += wG.x; acc[1] += wG.y; acc[2] += wG.z;
+        acc[3] += gq.x; acc[4] += gq.y; acc[5] += gq.z; acc[6] += gq.w;
+        acc[7] += wk * C.gr[g][0]; acc[8] += wk * C.gr[g][1]; acc[9] += wk * C.gr[g][2]; acc[10] += wk * C.gr[g][3];
+        acc[11] += wk * C.gs[g][0]; acc[12] += wk * C.gs[g][1]; acc[13] += wk * C.gs[g][2];
+        if (sk.mode != SKGS_LBS_W) {
+          const float dd2 = C.dl[g][mk];
+          acc[14] += -2.0f * dd2 * (p.x - pa.x);
+          acc[15] += -2.0f * dd2 * (p.y - pa.y);
+          acc[16] += -2.0f * dd2 * (p.z - pa.z);
+          acc[17] += C.e1[g][mk];
+          acc[18] += C.e2[g][mk];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (jactive) {
+#pragma unroll
+    for (int c = 0; c < NJ; c++)
+      if (acc[c] != 0.f) atomicAdd(&s_acc[NJ * ja + c], acc[c]);
+  }
+  __syncthreads();
+  for (int k = tid; k < M * NJ; k += blockDim.x) {
+    const float v = s_acc[k];
+    if (v != 0.f) atomicAdd(jacc + k, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // FK backward: one CTA.  Level-synchronous re-evaluation T_root = g, T_a = T_parent o L_a and its reverse sweep.
 // ------------------------------------------------------------------------------------------------------------------
@@ -706,7 +933,23 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
   cudaStream_t st = (cudaStream_t)stream;
   float* jacc = reinterpret_cast<float*>(workspace);
   SKGS_CUDA(cudaMemsetAsync(jacc, 0, skgs_fk_lbs_workspace_bytes(sk->M), st));
-  if (P > 0) {
+  if (P > 0 && sk->M <= JM_MAX_M) {
+    const size_t smem = lbs_bwd_jm_smem_bytes(sk->M);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_bwd_jm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    int grid = (P + JM_CHUNK - 1) / JM_CHUNK;
+    const int cap = fk_num_sms() * 2;
+    grid = grid > cap ? cap : grid;
+    {
+      ProfScope prof_("lbs_bwd_kernel", st);
+      lbs_bwd_jm_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
+                                                        dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
+      SKGS_CHECK_LAUNCH("lbs_bwd_jm_kernel");
+    }
+  } else if (P > 0) {
     const size_t smem = lbs_bwd_smem_bytes(sk->M);
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
@@ -720,7 +963,7 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
       ProfScope prof_("lbs_bwd_kernel", st);
       lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
                                                    dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
-    SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
+      SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
     }
   }
   {

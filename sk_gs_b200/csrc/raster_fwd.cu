@@ -60,7 +60,8 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
                        float2* __restrict__ means2D, float* __restrict__ depths, float* __restrict__ cov3Ds,
                        float4* __restrict__ conic_opacity, float4* __restrict__ rgbd, uint8_t* __restrict__ clamped,
                        uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ point_offsets,
-                       uint64_t* __restrict__ scan_state, skgs_raster_header* __restrict__ hdr, int num_blocks) {
+                       uint64_t* __restrict__ scan_state, skgs_raster_header* __restrict__ hdr, int num_blocks,
+                       uint32_t* __restrict__ tile_count) {
   __shared__ int s_bid;
   __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
   __shared__ uint32_t s_excl;
@@ -80,6 +81,7 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
   const float* Pm = s_P;
 
   uint32_t touched = 0;
+  int rx0 = 0, ry0 = 0, rx1 = 0;
   if (i < rp.P) {
     int my_rad = 0;
     const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
@@ -165,6 +167,7 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
         get_rect(pix_x, pix_y, irad, rp.gx, rp.gy, x0, y0, x1, y1);
         const int cnt = (x1 - x0) * (y1 - y0);
         if (cnt != 0) {
+          rx0 = x0; ry0 = y0; rx1 = x1;
           float rgb[3];
           uint8_t cl = 0;
           if (colors_precomp == nullptr) {
@@ -229,6 +232,23 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
     }
     radii[i] = my_rad;
     tiles_touched[i] = touched;
+  }
+  // ---- per-tile list lengths for the bucketed binning (one atomic per (Gaussian, tile) pair; rects with more than 32
+  //      tiles are walked by the whole warp)
+  if (tile_count != nullptr) {
+    const int lane_ = tid & 31;
+    const int w = rx1 - rx0;
+    if (touched > 0 && touched <= 32u)
+      for (uint32_t k = 0; k < touched; k++) atomicAdd(&tile_count[(ry0 + (int)k / w) * rp.gx + rx0 + (int)k % w], 1u);
+    uint32_t big = __ballot_sync(0xffffffffu, touched > 32u);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const int bx0 = __shfl_sync(0xffffffffu, rx0, src), by0 = __shfl_sync(0xffffffffu, ry0, src);
+      const int bw = __shfl_sync(0xffffffffu, w, src);
+      const uint32_t bc = __shfl_sync(0xffffffffu, touched, src);
+      for (uint32_t k = lane_; k < bc; k += 32) atomicAdd(&tile_count[(by0 + (int)k / bw) * rp.gx + bx0 + (int)k % bw], 1u);
+    }
   }
 
   // ---- block-inclusive scan of `touched`
@@ -540,7 +560,7 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, const skgs
 int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                            const float* opacities, const float* scales, const float* rotations,
                            const float* cov3D_precomp, char* geom, const skgs_raster_layout& lay, int32_t* radii,
-                           uint32_t* num_rendered_host, cudaStream_t st) {
+                           uint32_t* num_rendered_host, bool count_tiles, cudaStream_t st) {
   auto* hdr = reinterpret_cast<skgs_raster_header*>(geom + lay.header);
   const int nblocks = (rp.P + PRE_THREADS - 1) / PRE_THREADS;
   // header and scan_state are adjacent in the arena: one memset resets the ticket, the flags and the counters
@@ -554,7 +574,8 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
         reinterpret_cast<float*>(geom + lay.cov3D), reinterpret_cast<float4*>(geom + lay.conic_opacity),
         reinterpret_cast<float4*>(geom + lay.rgbd), reinterpret_cast<uint8_t*>(geom + lay.clamped),
         reinterpret_cast<uint32_t*>(geom + lay.tiles_touched), reinterpret_cast<uint32_t*>(geom + lay.point_offsets),
-        reinterpret_cast<uint64_t*>(geom + lay.scan_state), hdr, nblocks);
+        reinterpret_cast<uint64_t*>(geom + lay.scan_state), hdr, nblocks,
+        count_tiles ? reinterpret_cast<uint32_t*>(geom + lay.tile_count) : nullptr);
     SKGS_CHECK_LAUNCH("preprocess_scan_kernel");
     }
   }

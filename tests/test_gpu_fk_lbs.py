@@ -117,3 +117,25 @@ def test_assemble_forward_backward():
         assert (a.cpu().double() - b).abs().max().item() <= 2e-6
     for a, b in zip(gpu, cpu):
         assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) <= 1e-5
+
+
+def test_many_joints_uses_atomic_fallback():
+    """M > 256 takes the shared-memory-atomics LBS backward instead of the joint-major kernel; same results."""
+    M, P = 300, 3000
+    g = torch.Generator().manual_seed(41)
+    sc = S.make_scene('c1', P=P, seed=41)
+    parent = [-1] + [int(torch.randint(0, j, (1,), generator=g)) for j in range(1, M)]
+    sc.joints = torch.randn(M, 3, generator=g) * 0.6
+    sc.parents, sc.joint_depth, sc.root = S.find_root_table(parent)
+    sc.sk_r = torch.nn.functional.normalize(torch.randn(M, 4, generator=g), dim=-1)
+    sc.sk_d_rot, sc.sk_d_scale = 0.01 * torch.randn(M, 4, generator=g), 0.001 * torch.randn(M, 3, generator=g)
+    sc.sp_W = torch.randn(P, M, generator=g)
+    sc.sp_radius, sc.sp_weight = torch.full((M,), -1.5), torch.zeros(M)
+    for mode in ('W', 'weighted_kernel'):
+        cpu, gpu, o, gg = _run_both(sc, mode)
+        assert torch.equal(gg[8].cpu(), o[8])
+        cot = [torch.randn(t.shape, generator=g, dtype=torch.float64) for t in (o[0], o[1], o[2])]
+        sum((t * c).sum() for t, c in zip(o[:3], cot)).backward()
+        sum((t * c.float().to(t.device)).sum() for t, c in zip(gg[:3], cot)).backward()
+        for n in ['joints', 'sk_r', 'sk_d_rot', 'sk_d_scale', 'g_tr'] + (['sp_W'] if mode == 'W' else ['sp_radius', 'sp_weight']):
+            assert rel_err(gpu[n].grad.cpu().numpy(), cpu[n].grad.numpy()) <= GRAD_RTOL, (mode, n)

@@ -84,12 +84,13 @@ def test_preprocess_bit_exact(name, P, seed):
     assert st.num_rendered == b.R
 
 
+# debug bit 3 selects the experimental tile-bucketed binning instead of duplicate + onesweep (the default)
+@pytest.mark.parametrize('mode,flags', [('onesweep', 0), ('bucket', 8)])
 @pytest.mark.parametrize('name,P,seed', CASES)
-def test_binning_bit_exact(name, P, seed):
+def test_binning_bit_exact(name, P, seed, mode, flags):
     sc, net = _inputs(name, P, seed=seed)
     _, _, g, b = _oracle_forward(sc, net)
-    # emission order (test hook: stop after duplicate+sort is not possible, so compare the multiset per Gaussian run)
-    _, _, _, _, st = _gpu_forward(sc, net)
+    color, _, _, _, st = _gpu_forward(sc, net, debug_flags=flags)
     lay, R = st.layout, b.R
     keys = arena_view(st.binning, lay.keys_sorted, torch.int64, R).cpu().numpy().view(np.uint64)
     plist = arena_view(st.binning, lay.point_list, torch.int32, R).cpu().numpy().view(np.uint32)
@@ -98,7 +99,34 @@ def test_binning_bit_exact(name, P, seed):
     assert np.array_equal(keys, b.keys)
     assert np.array_equal(plist, b.point_list)
     assert np.array_equal(ranges, b.ranges)
-    assert np.all(np.diff(keys.astype(np.uint64)) >= 0) if R > 1 else True
+    # both binning paths feed the same compositing kernel: identical image bits
+    _, img, _, _ = _oracle_forward(sc, net)
+    assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
+
+
+def test_bucket_sort_out_of_core_and_depth_ties():
+    """Tiles with more than 8192 list entries take the chunked (shared + global) bitonic path; duplicated Gaussians give
+    exactly equal depths, whose order must be ascending Gaussian id (= emission order of the stable reference sort)."""
+    sc = S.make_scene('c1', P=12000, seed=17)
+    cam = sc.cameras[0]
+    cam.W, cam.H = 48, 40
+    cam.tanfovy = cam.tanfovx * cam.H / cam.W
+    sc.scaling = sc.scaling + 2.0
+    sc.xyz[6000:] = sc.xyz[:6000]  # exact duplicates (same skinning weights too) -> exact depth ties
+    sc.sp_W[6000:] = sc.sp_W[:6000]
+    net, _, _ = oracle_deform(sc)
+    net = {k: v.detach() for k, v in net.items()}
+    _, img, g, b = _oracle_forward(sc, net)
+    assert (b.ranges[:, 1] - b.ranges[:, 0]).max() > 8192
+    d = g.depths[b.point_list]
+    assert (np.diff(d) == 0).sum() > 1000
+    for flags in (0, 8):
+        color, _, _, _, st = _gpu_forward(sc, net, debug_flags=flags)
+        lay = st.layout
+        plist = arena_view(st.binning, lay.point_list, torch.int32, b.R).cpu().numpy().view(np.uint32)
+        keys = arena_view(st.binning, lay.keys_sorted, torch.int64, b.R).cpu().numpy().view(np.uint64)
+        assert np.array_equal(plist, b.point_list) and np.array_equal(keys, b.keys)
+        assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
 
 
 @pytest.mark.parametrize('name,P,seed', CASES)
