@@ -247,7 +247,8 @@ def run_ours(args, world, rank, local):
         peak, peak_src = measured_peak_hbm()
         for name, (n, us) in prof.items():
             per = us / n
-            gbs = ab.get(name, 0) / (per * 1e-6) / 1e9 if per > 0 else 0.0
+            key = 'onesweep_pass_kernel' if name.startswith('onesweep_pass') else name
+            gbs = ab.get(key, 0) / (per * 1e-6) / 1e9 if per > 0 else 0.0
             kern[name] = {'launches_per_step': n / nprof, 'us_per_launch': round(per, 3),
                           'us_per_step': round(us / nprof, 3), 'algorithmic_GBps': round(gbs, 1),
                           'frac_of_peak': round(gbs / peak, 4)}

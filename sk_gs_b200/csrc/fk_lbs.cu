@@ -172,12 +172,14 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(
 
 size_t fk_fwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 3 + 3 + 9 + 4 + 3 + 2) * sizeof(float); }
 
+template <int KT>  // KT = K as a compile-time constant (1..8): the K-list loops unroll without per-slot K tests
 __global__ void __launch_bounds__(FK_THREADS)
 fk_lbs_fwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, float* __restrict__ d_xyz,
                   float* __restrict__ d_rot, float* __restrict__ d_scale, float* __restrict__ sk_T,
                   float* __restrict__ weights, int64_t* __restrict__ indices) {
   extern __shared__ float fsm[];
-  const int M = sk.M, K = sk.K;
+  const int M = sk.M;
+  constexpr int K = KT;
   float* se0 = fsm;
   float* se1 = se0 + 7 * M;
   JointTable jt;
@@ -545,9 +547,14 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
           rank[k] = atomicAdd(&C.cnt[a], 1u);
         }
       if (sk.mode == SKGS_LBS_W) {
+        // dL/dsp_W is dense [P][M] with K non-zeros per row: the rows were zero-filled by a memset node, only the K
+        // logit gradients are scattered here
+        if (dL_dsp_W != nullptr) {
+          float* row = dL_dsp_W + (size_t)i * M;
 #pragma unroll
-        for (int k = 0; k < MAXK; k++)
-          if (k < K) C.dl[tid][k] = w[k] * (dw[k] - wdw);
+          for (int k = 0; k < MAXK; k++)
+            if (k < K) row[idx[k]] = w[k] * (dw[k] - wdw);
+        }
       } else {
         float d2[MAXK], e[MAXK];
         float S = 0.f;
@@ -601,18 +608,6 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
     for (int k = 0; k < MAXK; k++)
       if (myidx[k] >= 0) C.list[C.off[myidx[k]] + rank[k]] = (uint16_t)((tid << 3) | k);
     __syncthreads();
-    // ---------------------------------------------------------------- dL/dsp_W rows of the chunk, coalesced
-    if (sk.mode == SKGS_LBS_W && dL_dsp_W != nullptr) {
-      float* out = dL_dsp_W + (size_t)base * M;
-      for (int e = tid; e < n * M; e += blockDim.x) {
-        const int g = e / M, a = e - g * M;
-        float v = 0.f;
-#pragma unroll
-        for (int k = 0; k < MAXK; k++)
-          if (k < K && C.idx[g][k] == a) v = C.dl[g][k];
-        out[e] = v;
-      }
-    }
     // ---------------------------------------------------------------- phase 2: thread = (joint, slice)
     if (jactive) {  // thread (ja, js) takes every nslice-th pair of joint ja's list: all lanes do useful work
       const uint32_t beg = C.off[ja], cntj = C.cnt[ja];
@@ -903,18 +898,27 @@ int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, fl
   SKGS_CHECK_ARG(P == 0 || (xyz && d_xyz && d_rot && d_scale && weights && indices), "NULL per-Gaussian buffer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = fk_fwd_smem_bytes(sk->M);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    SKGS_CUDA(cudaFuncSetAttribute(fk_lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   int grid = (P + FK_THREADS - 1) / FK_THREADS;
   const int cap = fk_num_sms() * 4;
   grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
   {
     ProfScope prof_("fk_lbs_fwd_kernel", st);
-    fk_lbs_fwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices);
-  SKGS_CHECK_LAUNCH("fk_lbs_fwd_kernel");
+#define SKGS_FK_CASE(KK)                                                                                              \
+  case KK: {                                                                                                          \
+    static size_t smem_set = 0;                                                                                       \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                                        \
+      SKGS_CUDA(cudaFuncSetAttribute(fk_lbs_fwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                \
+    }                                                                                                                 \
+    fk_lbs_fwd_kernel<KK><<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices); \
+  } break;
+    switch (sk->K) {
+      SKGS_FK_CASE(1) SKGS_FK_CASE(2) SKGS_FK_CASE(3) SKGS_FK_CASE(4) SKGS_FK_CASE(5) SKGS_FK_CASE(6) SKGS_FK_CASE(7)
+      SKGS_FK_CASE(8)
+      default: break;
+    }
+#undef SKGS_FK_CASE
+    SKGS_CHECK_LAUNCH("fk_lbs_fwd_kernel");
   }
   return SKGS_OK;
 }
@@ -943,6 +947,8 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     int grid = (P + JM_CHUNK - 1) / JM_CHUNK;
     const int cap = fk_num_sms() * 2;
     grid = grid > cap ? cap : grid;
+    if (sk->mode == SKGS_LBS_W && dL_dsp_W != nullptr)
+      SKGS_CUDA(cudaMemsetAsync(dL_dsp_W, 0, (size_t)P * sk->M * sizeof(float), st));
     {
       ProfScope prof_("lbs_bwd_kernel", st);
       lbs_bwd_jm_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,

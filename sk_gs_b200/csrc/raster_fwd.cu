@@ -414,6 +414,23 @@ onesweep_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restric
   const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
+  // a digit that is constant over all keys (typically the sign/exponent byte of the depth) makes the pass the
+  // identity permutation: copy the tiles straight through, no ranking, no look-back
+  if (__syncthreads_or(n > 0 && hist[tid] == n)) {
+    while (true) {
+      if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+      __syncthreads();
+      const uint32_t tile = S.tile;
+      __syncthreads();
+      if (tile >= num_tiles) return;
+      const uint32_t base = tile * OS_TILE;
+      const uint32_t cnt = min((uint32_t)OS_TILE, n - base);
+      for (uint32_t k = tid; k < cnt; k += OS_THREADS) {
+        kout[base + k] = kin[base + k];
+        vout[base + k] = vin[base + k];
+      }
+    }
+  }
   // exclusive scan of the global digit histogram (256 values, one per thread)
   {
     const uint32_t c = hist[tid];
@@ -637,7 +654,9 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   uint32_t *vin = vA, *vout = vB;
   for (int p = 0; p < passes; p++) {
     {
-      ProfScope prof_("onesweep_pass_kernel", st);
+      static const char* kPassName[MAX_PASSES] = {"onesweep_pass0", "onesweep_pass1", "onesweep_pass2", "onesweep_pass3",
+                                                  "onesweep_pass4", "onesweep_pass5", "onesweep_pass6", "onesweep_pass7"};
+      ProfScope prof_(kPassName[p], st);
       onesweep_pass_kernel<<<grid, OS_THREADS, sizeof(OnesweepSmem), st>>>(kin, vin, kout, vout, hdr, (uint32_t)R_cap,
                                                                           hist + p * 256, status,
                                                                           &hdr->sort_ticket[p], 8 * p, (uint32_t)p);
