@@ -141,26 +141,32 @@ def run_ours(args, world, rank, local):
     params = list(hp.params.values())
 
     from sk_gs_b200.dist import GradArena, allreduce_max_
+    from sk_gs_b200.fk_lbs import scatter_sp_W_grad
     arena = None
     if world > 1:
-        shapes = {n: tuple(t.shape) for n, t in hp.params.items()}
-        shapes['viewspace_points'] = (cfg.P, 3)
-        arena = GradArena(shapes, dev)
+        # flat fp32 exchange buffer; the backward kernels write into it directly (no packing copies).  sp_W travels in
+        # compact [P, K] form (the KNN pattern is identical on every rank); SH gradients as one [P, 16, 3] block.
+        shapes = {'shs': (cfg.P, 16, 3), 'xyz': (cfg.P, 3), 'viewspace_points': (cfg.P, 3), 'scaling': (cfg.P, 3),
+                  'rotation': (cfg.P, 4), 'opacity': (cfg.P, 1), 'sp_W': (cfg.P, sc.K), 'joints': (cfg.M, 3),
+                  'sk_r': (cfg.M, 4), 'sk_d_rot': (cfg.M, 4), 'sk_d_scale': (cfg.M, 3), 'g_tr': (7,)}
+        arena = GradArena(shapes, dev, order=list(shapes))
+        dL_dev.mul_(1.0 / world)   # mean over the views of the step: folded into the upstream gradient
+        dL_host.mul_(1.0 / world)
 
     def exchange(out, grads):
-        """The one exchange step of a data-parallel iteration: SUM of all gradients (mean over views), MAX of radii."""
+        """The one exchange step of a data-parallel iteration: SUM of all gradients, MAX of radii."""
         if world == 1:
             return
-        arena.pack(grads)
-        arena.allreduce(scale=1.0 / world, chunks=2)
+        arena.allreduce(chunks=2)
         allreduce_max_(out['radii'])
+        scatter_sp_W_grad(arena.view('sp_W'), out['_sk'][8], cfg.M)  # dense [P, M] gradient for the optimizer
+
+    uploads = [(hp.params[n].data, t) for n, t in joint_host.items()] + \
+        [(rs.viewmatrix, cam_host['viewmatrix']), (rs.projmatrix, cam_host['projmatrix']), (rs.campos, cam_host['campos'])]
 
     def upload():
-        for n, t in joint_host.items():
-            hp.params[n].data.copy_(t, non_blocking=True)
-        rs.viewmatrix.copy_(cam_host['viewmatrix'], non_blocking=True)
-        rs.projmatrix.copy_(cam_host['projmatrix'], non_blocking=True)
-        rs.campos.copy_(cam_host['campos'], non_blocking=True)
+        for dst, src in uploads:
+            dst.copy_(src, non_blocking=True)
         dL_dev.copy_(dL_host, non_blocking=True)
 
     def download(img):
@@ -171,23 +177,34 @@ def run_ours(args, world, rank, local):
         return float(result_host[0])
 
     graph_state = {}
+    compact = world > 1
 
     def step(e2e: bool):
-        if e2e:
-            upload()
         if args.graph:
-            if 'g' not in graph_state:
-                graph_state['g'], graph_state['out'], graph_state['grads'] = hp.capture_step(view, dL_dev)
-            graph_state['g'].replay()
-            out, grads = graph_state['out'], graph_state['grads']
+            key = 'e2e' if e2e else 'dev'
+            if key not in graph_state:  # the e2e graph contains the host->device uploads, the device graph does not
+                graph_state[key] = hp.capture_step(view, dL_dev, compact_sp_W=compact,
+                                                   uploads=uploads if e2e else None, dL_host=dL_host if e2e else None,
+                                                   epilogue=exchange if world > 1 else None, arena=arena)
+            g, out, grads = graph_state[key]
+            g.replay()  # with N > 1 the NCCL all-reduces are nodes of the same graph
+            return download(out['images']) if e2e else None
         elif args.autograd:  # the drop-in autograd API (render_gs_offical + fk_lbs + assemble Functions)
+            if e2e:
+                upload()
             hp.zero_grad()
             out = hp.render(view)
             out['images'].backward(dL_dev)
             grads = dict(hp.grads())
             grads['viewspace_points'] = out['viewspace_points'].grad
+            if compact:
+                grads['sp_W'] = torch.gather(grads['sp_W'], 1, out['_sk'][8])
+                grads['shs'] = torch.cat((grads['f_dc'], grads['f_rest']), 1)
+                arena.pack(grads)
         else:
-            out, grads = hp.step_grads(view, dL_dev)
+            if e2e:
+                upload()
+            out, grads = hp.step_grads(view, dL_dev, compact_sp_W=compact, arena=arena)
         exchange(out, grads)
         return download(out['images']) if e2e else None
 

@@ -204,15 +204,17 @@ SKGS_API int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float
 /* Backward.  Incoming: dL_dd_xyz [P][3], dL_dd_rot [P][4], dL_dd_scale [P][3] (any may be NULL = zero), plus optional
  * direct gradients on the auxiliary outputs dL_dsk_T [M][7], dL_dweights [P][K] (NULL = zero).
  * Outgoing (NULL = not wanted): dL_djoints [M][3], dL_dsk_r [M][4], dL_dsk_d_rot [M][4], dL_dsk_d_scale [M][3],
- * dL_dg_tr [7], dL_dsp_W [P][M] (dense, K non-zeros per row), dL_dsp_radius [M], dL_dsp_weight [M].
+ * dL_dg_tr [7], dL_dsp_W [P][M] (dense, K non-zeros per row), dL_dsp_W_knn [P][K] (the same K values in KNN order -
+ * the compact form data-parallel ranks exchange, since the KNN pattern is identical on every rank),
+ * dL_dsp_radius [M], dL_dsp_weight [M].
  * workspace: device scratch of skgs_fk_lbs_workspace_bytes(M) bytes. */
 SKGS_API size_t skgs_fk_lbs_workspace_bytes(int32_t M);
 SKGS_API int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, const float* sk_T,
                                   const float* weights, const int64_t* indices, const float* dL_dd_xyz,
                                   const float* dL_dd_rot, const float* dL_dd_scale, const float* dL_dsk_T,
                                   const float* dL_dweights, float* dL_djoints, float* dL_dsk_r, float* dL_dsk_d_rot,
-                                  float* dL_dsk_d_scale, float* dL_dg_tr, float* dL_dsp_W, float* dL_dsp_radius,
-                                  float* dL_dsp_weight, void* workspace, void* stream);
+                                  float* dL_dsk_d_scale, float* dL_dg_tr, float* dL_dsp_W, float* dL_dsp_W_knn,
+                                  float* dL_dsp_radius, float* dL_dsp_weight, void* workspace, void* stream);
 
 /* Output assembly: points = _xyz + d_xyz, scales = exp(_scaling) + d_scale, rotations = normalize(_rotation + d_rot)
  * (eps 1e-12), opacity = sigmoid(_opacity).  d_* may be NULL (static stage). */

@@ -63,7 +63,7 @@ _SIGNATURES = {
                              [_vp] * 12),
     'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 8),
     'skgs_fk_lbs_workspace_bytes': (C.c_size_t, [_i32]),
-    'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 19),
+    'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),
     'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),
     'skgs_assemble_backward': (C.c_int, [_i32] + [_vp] * 16),
 }

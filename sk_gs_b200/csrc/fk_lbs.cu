@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(FK_THREADS)
 lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const float* __restrict__ sk_T,
                const float* __restrict__ weights, const int64_t* __restrict__ indices,
                const float* __restrict__ g_dxyz, const float* __restrict__ g_drot, const float* __restrict__ g_dscale,
-               const float* __restrict__ g_w, float* __restrict__ dL_dsp_W, float* __restrict__ jacc /*[M][NJ]*/) {
+               const float* __restrict__ g_w, float* __restrict__ dL_dsp_W, float* __restrict__ dL_dsp_W_knn,
+               float* __restrict__ jacc /*[M][NJ]*/) {
   extern __shared__ float bsm[];
   const int M = sk.M, K = sk.K;
   float* s_pos = bsm;             // [M][3]
@@ -380,6 +381,11 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
 #pragma unroll
         for (int k = 0; k < MAXK; k++)
           if (k < K) row[idx[k]] = w[k] * (dw[k] - wdw);
+      }
+      if (dL_dsp_W_knn != nullptr) {
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+          if (k < K) dL_dsp_W_knn[(size_t)i * K + k] = w[k] * (dw[k] - wdw);
       }
     } else {
       // u_k = e_k * s_k + 1e-7, w = u / S.  Recover S from the largest weight to avoid cancellation.
@@ -460,7 +466,7 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
                   const float* __restrict__ weights, const int64_t* __restrict__ indices,
                   const float* __restrict__ g_dxyz, const float* __restrict__ g_drot,
                   const float* __restrict__ g_dscale, const float* __restrict__ g_w, float* __restrict__ dL_dsp_W,
-                  float* __restrict__ jacc /*[M][NJ]*/) {
+                  float* __restrict__ dL_dsp_W_knn, float* __restrict__ jacc /*[M][NJ]*/) {
   extern __shared__ __align__(16) unsigned char jm_raw[];
   JmChunk& C = *reinterpret_cast<JmChunk*>(jm_raw);
   float* tab = reinterpret_cast<float*>(jm_raw + sizeof(JmChunk));
@@ -554,6 +560,11 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
 #pragma unroll
           for (int k = 0; k < MAXK; k++)
             if (k < K) row[idx[k]] = w[k] * (dw[k] - wdw);
+        }
+        if (dL_dsp_W_knn != nullptr) {  // compact form: the K logit gradients in KNN order
+#pragma unroll
+          for (int k = 0; k < MAXK; k++)
+            if (k < K) dL_dsp_W_knn[(size_t)i * K + k] = w[k] * (dw[k] - wdw);
         }
       } else {
         float d2[MAXK], e[MAXK];
@@ -929,7 +940,8 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
                          const int64_t* indices, const float* dL_dd_xyz, const float* dL_dd_rot,
                          const float* dL_dd_scale, const float* dL_dsk_T, const float* dL_dweights, float* dL_djoints,
                          float* dL_dsk_r, float* dL_dsk_d_rot, float* dL_dsk_d_scale, float* dL_dg_tr, float* dL_dsp_W,
-                         float* dL_dsp_radius, float* dL_dsp_weight, void* workspace, void* stream) {
+                         float* dL_dsp_W_knn, float* dL_dsp_radius, float* dL_dsp_weight, void* workspace,
+                         void* stream) {
   int rc = check_skeleton(sk, P);
   if (rc) return rc;
   SKGS_CHECK_ARG(workspace != nullptr && sk_T != nullptr, "workspace and sk_T are required");
@@ -952,7 +964,7 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     {
       ProfScope prof_("lbs_bwd_kernel", st);
       lbs_bwd_jm_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
-                                                        dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
+                                                        dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc);
       SKGS_CHECK_LAUNCH("lbs_bwd_jm_kernel");
     }
   } else if (P > 0) {
@@ -968,7 +980,7 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     {
       ProfScope prof_("lbs_bwd_kernel", st);
       lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
-                                                   dL_dd_scale, dL_dweights, dL_dsp_W, jacc);
+                                                   dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc);
       SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
     }
   }

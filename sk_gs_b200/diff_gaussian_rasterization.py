@@ -199,8 +199,9 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
     return color, depth, alpha, radii, state
 
 
-def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None):
-    """Returns dict of gradients (None where the input was absent)."""
+def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, out=None):
+    """Returns dict of gradients (None where the input was absent).  `out` may supply preallocated, contiguous fp32
+    tensors for any of the keys (e.g. views of a flat all-reduce arena); every output is fully overwritten."""
     L = _lib.lib()
     (view, proj, campos, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp) = state.keep
     device = means3D.device
@@ -212,13 +213,22 @@ def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=
     def new(*shape):
         return torch.empty(*shape, dtype=torch.float32, device=device)
 
+    out = out or {}
+
+    def pick(name, *shape):
+        t = out.get(name)
+        if t is None:
+            return new(*shape)
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == torch.Size(shape).numel(), name
+        return t
+
     g = {
-        'means3D': new(P, 3), 'means2D': new(P, 3), 'opacities': new(P, 1),
-        'shs': None if shs is None else new(P, M, 3),
-        'colors_precomp': None if colors_precomp is None else new(P, 3),
-        'scales': None if scales is None else new(P, 3),
-        'rotations': None if rotations is None else new(P, 4),
-        'cov3D_precomp': None if cov3D_precomp is None else new(P, 6),
+        'means3D': pick('means3D', P, 3), 'means2D': pick('means2D', P, 3), 'opacities': pick('opacities', P, 1),
+        'shs': None if shs is None else pick('shs', P, M, 3),
+        'colors_precomp': None if colors_precomp is None else pick('colors_precomp', P, 3),
+        'scales': None if scales is None else pick('scales', P, 3),
+        'rotations': None if rotations is None else pick('rotations', P, 4),
+        'cov3D_precomp': None if cov3D_precomp is None else pick('cov3D_precomp', P, 6),
     }
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream

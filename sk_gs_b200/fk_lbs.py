@@ -72,8 +72,9 @@ class _FkLbs(torch.autograd.Function):
         return _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w)
 
 
-def _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w):
+def _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w, out=None):
     if True:
+        out = out or {}
         L = _lib.lib()
         (xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, sk_r_delta, sk_T, weights,
          indices) = ctx.keep
@@ -84,9 +85,16 @@ def _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w):
         def new(*shape):
             return torch.empty(*shape, dtype=torch.float32, device=device)
 
-        d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale = new(M, 3), new(M, 4), new(M, 4), new(M, 3)
-        d_g_tr = None if g_tr is None else new(7)
-        d_sp_W = new(P, M) if (ctx.mode == 'W' and need[6]) else None
+        def pick(name, *shape):
+            t = out.get(name)
+            return new(*shape) if t is None else t
+
+        d_joints, d_sk_r = pick('joints', M, 3), pick('sk_r', M, 4)
+        d_sk_d_rot, d_sk_d_scale = pick('sk_d_rot', M, 4), pick('sk_d_scale', M, 3)
+        d_g_tr = None if g_tr is None else pick('g_tr', 7)
+        compact = bool(getattr(ctx, 'compact_sp_W', False))
+        d_sp_W = pick('sp_W', P, M) if (ctx.mode == 'W' and need[6] and not compact) else None
+        d_sp_W_knn = pick('sp_W', P, indices.shape[1]) if (ctx.mode == 'W' and need[6] and compact) else None
         d_sp_radius = new(M) if sp_radius is not None and ctx.mode in ('kernel', 'weighted_kernel') else None
         d_sp_weight = new(M) if sp_weight is not None and ctx.mode == 'weighted_kernel' else None
         ws = torch.empty(L.skgs_fk_lbs_workspace_bytes(M), dtype=torch.uint8, device=device)
@@ -98,10 +106,11 @@ def _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w):
                 _lib.ptr(None if g_dscale is None else _f32c(g_dscale)),
                 _lib.ptr(None if g_skT is None else _f32c(g_skT)), _lib.ptr(None if g_w is None else _f32c(g_w)),
                 d_joints.data_ptr(), d_sk_r.data_ptr(), d_sk_d_rot.data_ptr(), d_sk_d_scale.data_ptr(),
-                _lib.ptr(d_g_tr), _lib.ptr(d_sp_W), _lib.ptr(d_sp_radius), _lib.ptr(d_sp_weight), ws.data_ptr(), st),
+                _lib.ptr(d_g_tr), _lib.ptr(d_sp_W), _lib.ptr(d_sp_W_knn), _lib.ptr(d_sp_radius), _lib.ptr(d_sp_weight),
+                ws.data_ptr(), st),
                 'skgs_fk_lbs_backward')
-        return (None, d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight, None, None,
-                None, None, None, None)
+        return (None, d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W if not compact else d_sp_W_knn,
+                d_sp_radius, d_sp_weight, None, None, None, None, None, None)
 
 
 def fk_lbs(xyz: Tensor, joints: Tensor, sk_r: Tensor, sk_d_rot: Tensor, sk_d_scale: Tensor, g_tr: Optional[Tensor],
@@ -144,19 +153,23 @@ class _Assemble(torch.autograd.Function):
         return _assemble_backward_impl(ctx, gp, gs, gr, go)
 
 
-def _assemble_backward_impl(ctx, gp, gs, gr, go):
+def _assemble_backward_impl(ctx, gp, gs, gr, go, out=None):
     if True:
+        out = out or {}
         L = _lib.lib()
         scaling, rotation, opacity, d_rot = ctx.keep
         device = scaling.device
         P = scaling.shape[0]
         need = ctx.needs_input_grad
 
-        def new(like, cond):
-            return torch.empty_like(like) if cond else None
+        def new(like, cond, name=None):
+            if not cond:
+                return None
+            t = out.get(name) if name else None
+            return torch.empty_like(like) if t is None else t
 
-        dxyz, dscaling = new(scaling, need[0]), new(scaling, need[1])
-        drotation, dopacity = new(rotation, need[2]), new(opacity, need[3])
+        dxyz, dscaling = new(scaling, need[0], 'xyz'), new(scaling, need[1], 'scaling')
+        drotation, dopacity = new(rotation, need[2], 'rotation'), new(opacity, need[3], 'opacity')
         dd_xyz = new(scaling, ctx.has[0] and need[4])
         dd_rot = new(rotation, ctx.has[1] and need[5])
         dd_scale = new(scaling, ctx.has[2] and need[6])
@@ -198,9 +211,12 @@ def fk_lbs_forward_raw(xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, parents, r
     return out, ctx
 
 
-def fk_lbs_backward_raw(ctx, g_dxyz=None, g_drot=None, g_dscale=None, g_skT=None, g_w=None):
-    """-> (d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight)"""
-    r = _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w)
+def fk_lbs_backward_raw(ctx, g_dxyz=None, g_drot=None, g_dscale=None, g_skT=None, g_w=None, compact_sp_W=False,
+                        out=None):
+    """-> (d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight); with compact_sp_W the
+    sp_W gradient is returned as [P, K] (values in KNN order, see `scatter_sp_W_grad`) instead of dense [P, M]."""
+    ctx.compact_sp_W = compact_sp_W
+    r = _fk_lbs_backward_impl(ctx, g_dxyz, g_drot, g_dscale, g_skT, g_w, out)
     return r[1:9]
 
 
@@ -209,6 +225,15 @@ def assemble_forward_raw(xyz, scaling, rotation, opacity, d_xyz=None, d_rot=None
     return _Assemble.forward(ctx, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale), ctx
 
 
-def assemble_backward_raw(ctx, gp, gs, gr, go):
-    """-> (dxyz, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale)"""
-    return _assemble_backward_impl(ctx, gp, gs, gr, go)
+def assemble_backward_raw(ctx, gp, gs, gr, go, out=None, need=None):
+    """-> (dxyz, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale); `need` overrides which of the 7 are produced
+    (dL/d_xyz equals dL/dpoints, callers that already hold the latter can skip it)."""
+    if need is not None:
+        ctx.needs_input_grad = list(need)
+    return _assemble_backward_impl(ctx, gp, gs, gr, go, out)
+
+
+def scatter_sp_W_grad(d_knn: Tensor, indices: Tensor, M: int) -> Tensor:
+    """Expand the compact [P, K] logit gradients to the dense [P, M] gradient of sp_W."""
+    out = torch.zeros(d_knn.shape[0], M, dtype=d_knn.dtype, device=d_knn.device)
+    return out.scatter_(1, indices, d_knn)

@@ -74,7 +74,7 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
-    def step_grads(self, view: int, dL_dimage: Tensor):
+    def step_grads(self, view: int, dL_dimage: Tensor, compact_sp_W: bool = False, before_backward=None, arena=None):
         """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
         nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
         (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
@@ -93,12 +93,22 @@ class HotPath:
             sh = torch.cat((p['f_dc'], p['f_rest']), dim=1)
             color, depth, alpha, radii, st = DGR.rasterize_forward(self.settings[view], points, opacity, shs=sh,
                                                                    scales=scales, rotations=rotations, quat_wxyz=False)
-            g = DGR.rasterize_backward(st, dL_dimage)
-            dxyz, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
-                c2, g['means3D'], g['scales'], g['rotations'], g['opacities'])
+            if before_backward is not None:
+                before_backward()  # e.g. join the stream that uploads dL_dimage while the forward runs
+            # with an arena (sk_gs_b200.dist.GradArena) every final gradient is written straight into its slot of the
+            # flat all-reduce buffer: no packing copies before the exchange
+            A = (lambda n: arena.view(n)) if arena is not None else (lambda n: None)
+            g = DGR.rasterize_backward(st, dL_dimage, out={'means3D': A('xyz'), 'means2D': A('viewspace_points'),
+                                                          'shs': A('shs')})
+            _, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
+                c2, g['means3D'], g['scales'], g['rotations'], g['opacities'],
+                out={'scaling': A('scaling'), 'rotation': A('rotation'), 'opacity': A('opacity')},
+                need=[False, True, True, True, True, True, True])
+            dxyz = g['means3D']  # d points / d _xyz is the identity
             d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight = fk_lbs_backward_raw(
-                c1, dd_xyz, dd_rot, dd_scale)
-        grads = {'xyz': dxyz, 'scaling': dscaling, 'rotation': drotation, 'opacity': dopacity,
+                c1, dd_xyz, dd_rot, dd_scale, compact_sp_W=compact_sp_W,
+                out={n: A(n) for n in ('joints', 'sk_r', 'sk_d_rot', 'sk_d_scale', 'g_tr', 'sp_W')})
+        grads = {'xyz': dxyz, 'scaling': dscaling, 'rotation': drotation, 'opacity': dopacity, 'shs': g['shs'],
                  'f_dc': g['shs'][:, :1], 'f_rest': g['shs'][:, 1:], 'sp_W': d_sp_W, 'joints': d_joints, 'sk_r': d_sk_r,
                  'sk_d_rot': d_sk_d_rot, 'sk_d_scale': d_sk_d_scale, 'g_tr': d_g_tr, 'viewspace_points': g['means2D'],
                  'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight}
@@ -107,13 +117,14 @@ class HotPath:
                                                  weights, indices)}
         return out, grads
 
-    def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3):
+    def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3, compact_sp_W: bool = False,
+                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None):
         """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
         the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
         in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
         from . import _lib
         from . import diff_gaussian_rasterization as DGR
-        self.step_grads(view, dL_dimage)
+        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena)
         torch.cuda.synchronize(self.device)
         R = int(DGR.last_header_words(self.device)[0])
         DGR.set_fixed_capacity(int(R * headroom) + 4096)
@@ -121,13 +132,30 @@ class HotPath:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                self.step_grads(view, dL_dimage)
+                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena)
+                if epilogue is not None:
+                    epilogue(o_, g_)  # e.g. the NCCL gradient exchange: communicators must exist before capture
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
-            out, grads = self.step_grads(view, dL_dimage)
+            # optional host->device uploads captured INTO the graph: the small per-step inputs (camera, joint
+            # rotations) first, the large upstream gradient on a forked stream that is joined right before backward,
+            # so its PCIe time hides behind the forward kernels
+            join = None
+            for dst, src in (uploads or []):
+                dst.copy_(src, non_blocking=True)
+            if dL_host is not None:
+                main = torch.cuda.current_stream(self.device)
+                up = torch.cuda.Stream(self.device)
+                up.wait_stream(main)
+                with torch.cuda.stream(up):
+                    dL_dimage.copy_(dL_host, non_blocking=True)
+                join = lambda: main.wait_stream(up)  # noqa: E731
+            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, arena=arena)
+            if epilogue is not None:
+                epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
         torch.cuda.synchronize(self.device)
         return graph, out, grads
