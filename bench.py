@@ -154,12 +154,24 @@ def run_ours(args, world, rank, local):
         dL_host.mul_(1.0 / world)
 
     def exchange(out, grads):
-        """The one exchange step of a data-parallel iteration: SUM of all gradients, MAX of radii."""
+        """The one exchange step of a data-parallel iteration: SUM of all gradients (the MAX of the screen radii was
+        already started on a side stream right after the forward, see after_forward)."""
         if world == 1:
             return
-        arena.allreduce(chunks=2)
-        allreduce_max_(out['radii'])
+        arena.allreduce(chunks=1)  # one call: at 27 MB two chunks cost more latency than they overlap
         scatter_sp_W_grad(arena.view('sp_W'), out['_sk'][8], cfg.M)  # dense [P, M] gradient for the optimizer
+
+    side = torch.cuda.Stream(dev) if world > 1 else None
+
+    def after_forward(radii):
+        """radii are final after the forward: their MAX all-reduce runs on a side stream under the whole backward."""
+        if world == 1:
+            return None
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            allreduce_max_(radii)
+        return lambda: main.wait_stream(side)
 
     uploads = [(hp.params[n].data, t) for n, t in joint_host.items()] + \
         [(rs.viewmatrix, cam_host['viewmatrix']), (rs.projmatrix, cam_host['projmatrix']), (rs.campos, cam_host['campos'])]
@@ -185,7 +197,8 @@ def run_ours(args, world, rank, local):
             if key not in graph_state:  # the e2e graph contains the host->device uploads, the device graph does not
                 graph_state[key] = hp.capture_step(view, dL_dev, compact_sp_W=compact,
                                                    uploads=uploads if e2e else None, dL_host=dL_host if e2e else None,
-                                                   epilogue=exchange if world > 1 else None, arena=arena)
+                                                   epilogue=exchange if world > 1 else None, arena=arena,
+                                                   after_forward=after_forward if world > 1 else None)
             g, out, grads = graph_state[key]
             g.replay()  # with N > 1 the NCCL all-reduces are nodes of the same graph
             return download(out['images']) if e2e else None
@@ -201,10 +214,12 @@ def run_ours(args, world, rank, local):
                 grads['sp_W'] = torch.gather(grads['sp_W'], 1, out['_sk'][8])
                 grads['shs'] = torch.cat((grads['f_dc'], grads['f_rest']), 1)
                 arena.pack(grads)
+                allreduce_max_(out['radii'])
         else:
             if e2e:
                 upload()
-            out, grads = hp.step_grads(view, dL_dev, compact_sp_W=compact, arena=arena)
+            out, grads = hp.step_grads(view, dL_dev, compact_sp_W=compact, arena=arena,
+                                       after_forward=after_forward if world > 1 else None)
         exchange(out, grads)
         return download(out['images']) if e2e else None
 
@@ -243,6 +258,29 @@ def run_ours(args, world, rank, local):
     ms_dev, launches = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(True, args.steps, max(args.warmup, 3))
+
+    # ---- render FPS (forward only, the reference's test.py --fps protocol: CUDA events around N renders, no_grad)
+    fps = None
+    if rank == 0:
+        with torch.no_grad():
+            for _ in range(3):
+                hp.render(view)
+            torch.cuda.synchronize()
+            gfps = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gfps):
+                hp.render(view)
+            torch.cuda.synchronize()
+            nf = max(50, args.steps)
+            evs = []
+            for _ in range(nf):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                gfps.replay()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            fps = round(nf / (sum(a.elapsed_time(b) for a, b in evs) * 1e-3), 1)
 
     # ---- per-kernel device times for the roofline (separate pass, events around every launch)
     kern = {}
@@ -300,6 +338,7 @@ def run_ours(args, world, rank, local):
                                           sum(t.numel() for t in cam_host.values()) * 4),
                 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
+        'render_fps': {'value': fps, 'unit': 'frames/s', 'note': 'forward only (FK+LBS+assembly+rasterize), 1 GPU, CUDA graph'},
         'roofline': roofline,
         'kernels': kern,
         'cpu_baseline': cpu,
@@ -459,6 +498,9 @@ def main():
     world, rank, local = _dist()
     if world > 1:
         import torch.distributed as dist
+        # measured on the 8xB200 NVSwitch box for the 26.8 MB gradient arena (tools/ar_sweep.sh): Ring 111 us,
+        # default (NVLS) 140 us, Tree 158 us
+        os.environ.setdefault('NCCL_ALGO', 'Ring')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29511')
         torch.cuda.set_device(local)

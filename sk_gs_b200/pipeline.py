@@ -74,7 +74,8 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
-    def step_grads(self, view: int, dL_dimage: Tensor, compact_sp_W: bool = False, before_backward=None, arena=None):
+    def step_grads(self, view: int, dL_dimage: Tensor, compact_sp_W: bool = False, before_backward=None, arena=None,
+                   after_forward=None):
         """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
         nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
         (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
@@ -93,6 +94,7 @@ class HotPath:
             sh = torch.cat((p['f_dc'], p['f_rest']), dim=1)
             color, depth, alpha, radii, st = DGR.rasterize_forward(self.settings[view], points, opacity, shs=sh,
                                                                    scales=scales, rotations=rotations, quat_wxyz=False)
+            join_after = after_forward(radii) if after_forward is not None else None  # e.g. radii MAX on a side stream
             if before_backward is not None:
                 before_backward()  # e.g. join the stream that uploads dL_dimage while the forward runs
             # with an arena (sk_gs_b200.dist.GradArena) every final gradient is written straight into its slot of the
@@ -112,19 +114,21 @@ class HotPath:
                  'f_dc': g['shs'][:, :1], 'f_rest': g['shs'][:, 1:], 'sp_W': d_sp_W, 'joints': d_joints, 'sk_r': d_sk_r,
                  'sk_d_rot': d_sk_d_rot, 'sk_d_scale': d_sk_d_scale, 'g_tr': d_g_tr, 'viewspace_points': g['means2D'],
                  'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight}
+        if join_after is not None:
+            join_after()
         out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
                'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, p['sk_d_rot'], p['sk_d_scale'], p['g_tr'],
                                                  weights, indices)}
         return out, grads
 
     def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3, compact_sp_W: bool = False,
-                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None):
+                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None, after_forward=None):
         """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
         the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
         in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
         from . import _lib
         from . import diff_gaussian_rasterization as DGR
-        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena)
+        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward)
         torch.cuda.synchronize(self.device)
         R = int(DGR.last_header_words(self.device)[0])
         DGR.set_fixed_capacity(int(R * headroom) + 4096)
@@ -132,7 +136,7 @@ class HotPath:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena)
+                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward)
                 if epilogue is not None:
                     epilogue(o_, g_)  # e.g. the NCCL gradient exchange: communicators must exist before capture
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -153,7 +157,8 @@ class HotPath:
                 with torch.cuda.stream(up):
                     dL_dimage.copy_(dL_host, non_blocking=True)
                 join = lambda: main.wait_stream(up)  # noqa: E731
-            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, arena=arena)
+            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, arena=arena,
+                                         after_forward=after_forward)
             if epilogue is not None:
                 epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
