@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libskgs_b200.so')
+LIB_PATH = os.environ.get('SKGS_LIB', os.path.join(_HERE, 'libskgs_b200.so'))  # SKGS_LIB: tuning builds (tools/)
 
 c_f32p = C.c_void_p  # all device pointers travel as integers (tensor.data_ptr())
 

@@ -48,7 +48,7 @@ void prof_end(cudaStream_t st) {
 
 int sort_passes(int gx, int gy);
 
-constexpr int OS_TILE_KEYS = 4096;  // must match OS_TILE in raster_fwd.cu
+constexpr int OS_TILE_KEYS = 2048;  // lower bound of OS_TILE in raster_fwd.cu (sizes the look-back words)
 constexpr size_t ARENA_ALIGN = 256;
 
 static int fill_params(const skgs_raster_settings* s, int P, int M, RasterParams& rp) {

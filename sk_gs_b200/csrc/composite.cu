@@ -24,7 +24,16 @@
 
 namespace skgs {
 
-constexpr int CW_WARPS = 4;                 // warps per CTA (independent workers)
+#ifndef SKGS_CW_WARPS
+#define SKGS_CW_WARPS 4
+#endif
+#ifndef SKGS_BWD_MINBLOCKS
+#define SKGS_BWD_MINBLOCKS 6
+#endif
+#ifndef SKGS_RSLOTS
+#define SKGS_RSLOTS 6
+#endif
+constexpr int CW_WARPS = SKGS_CW_WARPS;     // warps per CTA (independent workers)
 constexpr int CW_THREADS = CW_WARPS * 32;
 constexpr int NGRAD = 12;                   // packed per-Gaussian accumulators: mx my ca cb | cc op z - | r g b -
 constexpr float PARKED = 1.0e18f;           // x coordinate of a finished pixel: its exponent is -inf
@@ -151,7 +160,7 @@ __device__ __forceinline__ bool footprint_may_hit(const float4 g0, const float4 
 // forward.  Work item = 8 x 4 pixels (one pixel per lane), 8 items per tile.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ITEM_W = 8, ITEM_H = 4, ITEMS_PER_TILE = (TILE / ITEM_W) * (TILE / ITEM_H);
-constexpr int RSLOTS = 6, RVALS = 10, RSTRIDE = 33;  // backward reduction staging (see composite_bwd_kernel)
+constexpr int RSLOTS = SKGS_RSLOTS, RVALS = 10, RSTRIDE = 33;  // backward reduction staging (see composite_bwd_kernel)
 
 __global__ void __launch_bounds__(CW_THREADS)
 composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
@@ -298,7 +307,7 @@ __device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(CW_THREADS)
+__global__ void __launch_bounds__(CW_THREADS, SKGS_BWD_MINBLOCKS)
 composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
                      uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,

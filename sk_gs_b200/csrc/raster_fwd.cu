@@ -383,8 +383,14 @@ duplicate_keys_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, 
 // ------------------------------------------------------------------------------------------------------------------
 // K3: onesweep radix pass (8-bit digit), stable.  Status word: [31:29] pass tag, [28:27] flag, [26:0] count.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int OS_THREADS = 256;
-constexpr int OS_ITEMS = 16;
+#ifndef SKGS_OS_THREADS
+#define SKGS_OS_THREADS 256
+#endif
+#ifndef SKGS_OS_ITEMS
+#define SKGS_OS_ITEMS 24
+#endif
+constexpr int OS_THREADS = SKGS_OS_THREADS;
+constexpr int OS_ITEMS = SKGS_OS_ITEMS;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // 4096 keys per tile
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr uint32_t OS_FLAG_AGG = 1u, OS_FLAG_INC = 2u;
