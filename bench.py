@@ -308,9 +308,16 @@ def run_ours(args, world, rank, local):
                           'us_per_step': round(us / nprof, 3), 'algorithmic_GBps': round(gbs, 1),
                           'frac_of_peak': round(gbs / peak, 4)}
         dom = max(kern, key=lambda k: kern[k]['us_per_step'])
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_roofline_traffic.json')
+        if os.path.exists(tpath) and args.workload == 'c2':
+            with open(tpath) as f:
+                tj = json.load(f).get(dom)
+            if tj:
+                traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']  # bytes per launch, one ncu --set full capture
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['algorithmic_GBps'], 'peak': peak,
                     'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['frac_of_peak'],
-                    'traffic': None,
+                    'traffic': traffic, 'algorithmic_bytes': ab.get(dom),
                     'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel; compositing is FP32-issue '
                             'bound (about 145 flop/B), see DESIGN.md'}
     if rank != 0:

@@ -431,9 +431,25 @@ onesweep_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restric
       if (tile >= num_tiles) return;
       const uint32_t base = tile * OS_TILE;
       const uint32_t cnt = min((uint32_t)OS_TILE, n - base);
-      for (uint32_t k = tid; k < cnt; k += OS_THREADS) {
-        kout[base + k] = kin[base + k];
-        vout[base + k] = vin[base + k];
+      for (uint32_t k0 = tid; k0 < cnt; k0 += 4 * OS_THREADS) {  // four independent loads in flight per thread
+        uint64_t kk[4];
+        uint32_t vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t k = k0 + u * OS_THREADS;
+          if (k < cnt) {
+            kk[u] = kin[base + k];
+            vv[u] = vin[base + k];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t k = k0 + u * OS_THREADS;
+          if (k < cnt) {
+            kout[base + k] = kk[u];
+            vout[base + k] = vv[u];
+          }
+        }
       }
     }
   }
