@@ -140,7 +140,7 @@ def run_ours(args, world, rank, local):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     params = list(hp.params.values())
 
-    from sk_gs_b200.dist import GradArena, allreduce_max_
+    from sk_gs_b200.dist import GradArena, SymmGradArena, allreduce_max_
     from sk_gs_b200.fk_lbs import scatter_sp_W_grad
     arena = None
     if world > 1:
@@ -149,7 +149,9 @@ def run_ours(args, world, rank, local):
         shapes = {'shs': (cfg.P, 16, 3), 'xyz': (cfg.P, 3), 'viewspace_points': (cfg.P, 3), 'scaling': (cfg.P, 3),
                   'rotation': (cfg.P, 4), 'opacity': (cfg.P, 1), 'sp_W': (cfg.P, sc.K), 'joints': (cfg.M, 3),
                   'sk_r': (cfg.M, 4), 'sk_d_rot': (cfg.M, 4), 'sk_d_scale': (cfg.M, 3), 'g_tr': (7,)}
-        arena = GradArena(shapes, dev, order=list(shapes))
+        arena = (GradArena if args.allreduce == 'nccl' else SymmGradArena)(shapes, dev, order=list(shapes))
+        exchange_kind = 'NVLS multimem all-reduce kernel (symmetric memory)' if getattr(arena, 'multimem', False) \
+            else 'NCCL all-reduce'
         dL_dev.mul_(1.0 / world)   # mean over the views of the step: folded into the upstream gradient
         dL_host.mul_(1.0 / world)
 
@@ -158,7 +160,10 @@ def run_ours(args, world, rank, local):
         already started on a side stream right after the forward, see after_forward)."""
         if world == 1:
             return
-        arena.allreduce(chunks=1)  # one call: at 27 MB two chunks cost more latency than they overlap
+        if split_exchange:  # the rasterizer-side blocks were reduced under the LBS / FK backward (mid_backward)
+            arena.allreduce_range(arena.block_start('sp_W'), arena.flat_padded.numel(), channel=1)
+        else:
+            arena.allreduce(chunks=1)  # one call: at 27 MB two NCCL chunks cost more latency than they overlap
         scatter_sp_W_grad(arena.view('sp_W'), out['_sk'][8], cfg.M)  # dense [P, M] gradient for the optimizer
 
     side = torch.cuda.Stream(dev) if world > 1 else None
@@ -172,6 +177,18 @@ def run_ours(args, world, rank, local):
         with torch.cuda.stream(side):
             allreduce_max_(radii)
         return lambda: main.wait_stream(side)
+
+    split_exchange = world > 1 and getattr(arena, 'multimem', False)
+    side2 = torch.cuda.Stream(dev) if split_exchange else None
+
+    def mid_backward():
+        """Called when every rasterizer-side gradient (SH, means, scales, rotations, opacity: 92 % of the bytes) is final:
+        their in-switch reduction runs on a side stream while the LBS and FK backward kernels execute."""
+        main = torch.cuda.current_stream(dev)
+        side2.wait_stream(main)
+        with torch.cuda.stream(side2):
+            arena.allreduce_range(0, arena.block_start('sp_W'), channel=0)
+        return lambda: main.wait_stream(side2)
 
     uploads = [(hp.params[n].data, t) for n, t in joint_host.items()] + \
         [(rs.viewmatrix, cam_host['viewmatrix']), (rs.projmatrix, cam_host['projmatrix']), (rs.campos, cam_host['campos'])]
@@ -198,7 +215,8 @@ def run_ours(args, world, rank, local):
                 graph_state[key] = hp.capture_step(view, dL_dev, compact_sp_W=compact,
                                                    uploads=uploads if e2e else None, dL_host=dL_host if e2e else None,
                                                    epilogue=exchange if world > 1 else None, arena=arena,
-                                                   after_forward=after_forward if world > 1 else None)
+                                                   after_forward=after_forward if world > 1 else None,
+                                                   mid_backward=mid_backward if split_exchange else None)
             g, out, grads = graph_state[key]
             g.replay()  # with N > 1 the NCCL all-reduces are nodes of the same graph
             return download(out['images']) if e2e else None
@@ -219,7 +237,8 @@ def run_ours(args, world, rank, local):
             if e2e:
                 upload()
             out, grads = hp.step_grads(view, dL_dev, compact_sp_W=compact, arena=arena,
-                                       after_forward=after_forward if world > 1 else None)
+                                       after_forward=after_forward if world > 1 else None,
+                                       mid_backward=mid_backward if split_exchange else None)
         exchange(out, grads)
         return download(out['images']) if e2e else None
 
@@ -334,7 +353,7 @@ def run_ours(args, world, rank, local):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{cfg.name}: {cfg.P} Gaussians, {cfg.M} joints, {W}x{H}, 1 view per GPU, SH degree 3, '
                                f'K=5 LBS mode W, fwd+bwd', 'num_rendered': R, 'views_per_step': world,
-                   'parallelism': f'view-sharded dp{world}' + (' + NCCL grad allreduce' if world > 1 else ''),
+                   'parallelism': f'view-sharded dp{world}' + (f' + {exchange_kind}' if world > 1 else ''),
                    'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs',
                    'launch': 'CUDA graph replay (fixed binning capacity, overflow flag checked)' if args.graph
                    else ('eager launches through the autograd API' if args.autograd else 'eager launches')},
@@ -497,6 +516,8 @@ def main():
     ap.add_argument('--ref-device', default='auto', choices=['auto', 'cpu', 'cuda'])
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
+                    help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
     ap.add_argument('--autograd', action='store_true', help='with --no-graph: time the drop-in autograd API path')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='launch every step eagerly instead of replaying a captured CUDA graph')

@@ -227,6 +227,15 @@ SKGS_API int skgs_assemble_backward(int32_t P, const float* scaling, const float
                                     float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_xyz,
                                     float* dL_dd_rot, float* dL_dd_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange
+ * ------------------------------------------------------------------------------------------------------------- */
+/* In-switch all-reduce (SUM, in place) of a flat fp32 arena that lives in symmetric memory bound to one NVLS multicast
+ * address (`multicast_ptr`, e.g. from torch.distributed._symmetric_memory).  Rank `rank` reduces and re-broadcasts the
+ * rank-th slice with multimem.ld_reduce / multimem.st.  The caller brackets the call with cross-GPU barriers on the
+ * same stream.  The reference has no counterpart (its DDP wiring is unused, my_ext/framework.py:339-357). */
+SKGS_API int skgs_multimem_allreduce(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ _SIGNATURES = {
     'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),
     'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),
     'skgs_assemble_backward': (C.c_int, [_i32] + [_vp] * 16),
+    'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -42,7 +42,7 @@ class GradArena:
         for n in self.names:
             k = self.shapes[n].numel()
             self.offsets[n] = (o, o + k)
-            o += k
+            o = (o + k + 3) // 4 * 4  # every block starts on a 16-byte boundary (vector all-reduce of sub-ranges)
         self.flat = torch.zeros(o, dtype=torch.float32, device=device)
 
     def view(self, name: str) -> Tensor:
@@ -80,6 +80,53 @@ class GradArena:
 
     def unpack(self) -> Dict[str, Tensor]:
         return {n: self.view(n) for n in self.names}
+
+
+class SymmGradArena(GradArena):
+    """GradArena whose flat buffer is symmetric memory (same allocation on every GPU of the box, one NVLS multicast
+    address).  `allreduce()` is then ONE kernel of libskgs_b200.so (multimem.ld_reduce + multimem.st: the NVSwitch sums
+    and broadcasts, 1/N of the arena crosses each GPU's links) bracketed by two signal-pad barriers - instead of NCCL's
+    ring (2(N-1)/N of the arena per GPU plus protocol latency).  torch's symmetric-memory module is used only for the
+    plumbing: allocation, rendezvous, barriers.  Falls back to the NCCL path of the base class when multicast is not
+    available (`self.multimem` tells which one is active)."""
+
+    def __init__(self, shapes, device, order=None, group=None):
+        super().__init__(shapes, device, order)
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        n = (self.flat.numel() + 3) // 4 * 4
+        buf = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(buf, self.group.group_name)
+        buf.zero_()
+        self.flat_padded = buf
+        self.flat = buf[:self.flat.numel()]
+        self.multimem = bool(self.handle.multicast_ptr)
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+
+    def allreduce(self, scale: float = 1.0, group=None, chunks: int = 1, async_op: bool = False):
+        if not self.multimem:
+            return super().allreduce(scale, group, chunks, async_op)
+        if scale != 1.0:
+            self.flat.mul_(scale)
+        self.allreduce_range(0, self.flat_padded.numel())
+        return []
+
+    def allreduce_range(self, start: int, stop: int, channel: int = 0):
+        """SUM over ranks of flat[start:stop] (both multiples of 4) on the CURRENT stream; `channel` selects the pair of
+        signal-pad barriers so that two ranges can be in flight on different streams."""
+        from . import _lib
+        if not self.multimem:
+            dist.all_reduce(self.flat_padded[start:stop], group=self.group)
+            return
+        assert start % 4 == 0 and stop % 4 == 0 and 0 <= start <= stop <= self.flat_padded.numel()
+        st = torch.cuda.current_stream(self.flat.device).cuda_stream
+        self.handle.barrier(channel=2 * channel)      # every rank's producers of this range have finished
+        _lib.check(_lib.lib().skgs_multimem_allreduce(self.handle.multicast_ptr + 4 * start, stop - start, self.rank,
+                                                      self.world, st), 'skgs_multimem_allreduce')
+        self.handle.barrier(channel=2 * channel + 1)  # every slice has been reduced and broadcast
+
+    def block_start(self, name: str) -> int:
+        return self.offsets[name][0]
 
 
 def allreduce_max_(t: Tensor, group=None) -> Tensor:

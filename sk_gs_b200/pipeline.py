@@ -75,7 +75,7 @@ class HotPath:
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def step_grads(self, view: int, dL_dimage: Tensor, compact_sp_W: bool = False, before_backward=None, arena=None,
-                   after_forward=None):
+                   after_forward=None, mid_backward=None):
         """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
         nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
         (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
@@ -107,6 +107,7 @@ class HotPath:
                 out={'scaling': A('scaling'), 'rotation': A('rotation'), 'opacity': A('opacity')},
                 need=[False, True, True, True, True, True, True])
             dxyz = g['means3D']  # d points / d _xyz is the identity
+            join_mid = mid_backward() if mid_backward is not None else None  # all rasterizer-side gradients are final
             d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight = fk_lbs_backward_raw(
                 c1, dd_xyz, dd_rot, dd_scale, compact_sp_W=compact_sp_W,
                 out={n: A(n) for n in ('joints', 'sk_r', 'sk_d_rot', 'sk_d_scale', 'g_tr', 'sp_W')})
@@ -116,19 +117,23 @@ class HotPath:
                  'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight}
         if join_after is not None:
             join_after()
+        if join_mid is not None:
+            join_mid()
         out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
                'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, p['sk_d_rot'], p['sk_d_scale'], p['g_tr'],
                                                  weights, indices)}
         return out, grads
 
     def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3, compact_sp_W: bool = False,
-                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None, after_forward=None):
+                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None, after_forward=None,
+                     mid_backward=None):
         """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
         the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
         in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
         from . import _lib
         from . import diff_gaussian_rasterization as DGR
-        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward)
+        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward,
+                        mid_backward=mid_backward)
         torch.cuda.synchronize(self.device)
         R = int(DGR.last_header_words(self.device)[0])
         DGR.set_fixed_capacity(int(R * headroom) + 4096)
@@ -136,7 +141,8 @@ class HotPath:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward)
+                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward,
+                                         mid_backward=mid_backward)
                 if epilogue is not None:
                     epilogue(o_, g_)  # e.g. the NCCL gradient exchange: communicators must exist before capture
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -158,7 +164,7 @@ class HotPath:
                     dL_dimage.copy_(dL_host, non_blocking=True)
                 join = lambda: main.wait_stream(up)  # noqa: E731
             out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, arena=arena,
-                                         after_forward=after_forward)
+                                         after_forward=after_forward, mid_backward=mid_backward)
             if epilogue is not None:
                 epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
