@@ -514,7 +514,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2')
     ap.add_argument('--ref-device', default='auto', choices=['auto', 'cpu', 'cuda'])
-    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--cpu-steps', type=int, default=40,
+                    help='bounded CPU sample: full fwd+bwd oracle steps of the same workload (about 10-20 s of host time)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
                     help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
@@ -524,6 +525,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world, rank, local = _dist()
+    if args.impl == 'reference':
+        # rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work (no process group needed)
+        if rank == 0:
+            run_reference(args, world, rank, local)
+        return
     if world > 1:
         import torch.distributed as dist
         # measured on the 8xB200 NVSwitch box for the 26.8 MB gradient arena (tools/ar_sweep.sh): Ring 111 us,
@@ -534,10 +540,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     try:
-        if args.impl == 'reference':
-            run_reference(args, world, rank, local)
-        else:
-            run_ours(args, world, rank, local)
+        run_ours(args, world, rank, local)
     finally:
         if world > 1:
             import torch.distributed as dist
