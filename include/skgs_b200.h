@@ -228,6 +228,58 @@ SKGS_API int skgs_assemble_backward(int32_t P, const float* scaling, const float
                                     float* dL_dd_rot, float* dL_dd_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Widening rows: the step after the path (photometric loss) and the step after that (Adam)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* loss = w_image * mean|I-G| (method 0; method 1: mean (I-G)^2) + w_ssim * (1 - mean SSIM_11x11(I, G)) and its gradient
+ * w.r.t. the rendered image, times grad_scale.  Replaces ImageLoss.forward (networks/losses/image_loss.py:20-33, unmasked),
+ * SSIM_Loss.forward + _ssim (networks/losses/ssim.py:27-62) and their autograd, called at networks/sk_gs.py:1528-1529
+ * with the weights of exps/default.yaml:83-84.
+ *   image  [3,H,W] channel-major (the rasterizer's output);
+ *   target [3,H,W] if target_pixel_stride == 0, else pixel-major [H,W,stride] with stride 3 or 4 (RGB of an RGBA image);
+ *   workspace: skgs_image_loss_workspace_bytes(H, W) bytes;
+ *   loss_terms float[3] (device): {pixel term, 1 - mean SSIM, weighted total};
+ *   dL_dimage [3,H,W] or NULL (forward only). */
+SKGS_API size_t skgs_image_loss_workspace_bytes(int32_t H, int32_t W);
+SKGS_API int skgs_image_loss(int32_t H, int32_t W, const float* image, const float* target, int32_t target_pixel_stride,
+                             int32_t method, float w_image, float w_ssim, float grad_scale, void* workspace,
+                             float* loss_terms, float* dL_dimage, void* stream);
+
+/* One Adam step over up to SKGS_ADAM_MAX_TENSORS parameter tensors in ONE launch (torch.optim.Adam semantics, no weight
+ * decay, no amsgrad - the optimizer the reference builds at networks/gaussian_splatting.py:445-453 with
+ * exps/default.yaml:121-125 eps 1e-15, betas (0.9, 0.999)):
+ *   m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).
+ * A tensor with `knn_indices != NULL` has its gradient in compact form: `grad` is [rows, K], `knn_indices` int64
+ * [rows, K] names the columns of the [rows, cols] parameter that receive it (the skinning-weight table sp_W, whose
+ * gradient has K non-zeros per row, networks/sk_gs.py:767-768); all other entries of the row see g = 0, exactly as the
+ * dense torch optimizer does.
+ * `dynamic_hyper` (device float[1 + 2 count], may be NULL) = {sqrt(1 - beta2^step), then per tensor lr_i / (1 - beta1^step)
+ * and lr2_i / (1 - beta1^step)}: when
+ * given it overrides `step` and `lr`, so that a captured CUDA graph can be replayed with the values of the current
+ * iteration (uploaded by the caller) instead of the ones frozen at capture time. */
+#define SKGS_ADAM_MAX_TENSORS 16
+typedef struct skgs_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;              /* rows * cols for a compact-gradient tensor */
+  double lr;
+  double lr2;                 /* see period */
+  int32_t period;             /* 0: every element uses lr.  > 0: element i uses lr if i % period < split, else lr2 - two
+                                 interleaved param groups stored as one array, e.g. the SH coefficients [P,16,3] whose
+                                 first 3 of every 48 floats are f_dc (lr_feature) and the rest f_rest (lr_feature / 20,
+                                 networks/gaussian_splatting.py:448-449); removes the per-step cat(f_dc, f_rest) */
+  int32_t split;
+  int32_t cols;               /* compact gradient only */
+  int32_t K;                  /* compact gradient only */
+  const int64_t* knn_indices; /* NULL = dense gradient */
+} skgs_adam_tensor;
+SKGS_API int skgs_adam_step(const skgs_adam_tensor* tensors /* host */, int32_t count, int32_t step, double beta1,
+                            double beta2, double eps, float grad_scale, const float* dynamic_hyper,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange
  * ------------------------------------------------------------------------------------------------------------- */
 /* In-switch all-reduce (SUM, in place) of a flat fp32 arena that lives in symmetric memory bound to one NVLS multicast

@@ -43,6 +43,15 @@ class Skeleton(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [
+        ('param', C.c_void_p), ('grad', C.c_void_p), ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p),
+        ('numel', C.c_int64), ('lr', C.c_double), ('lr2', C.c_double), ('period', C.c_int32), ('split', C.c_int32),
+        ('cols', C.c_int32), ('K', C.c_int32), ('knn_indices', C.c_void_p),
+    ]
+
+
+ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
 
 # every symbol include/skgs_b200.h declares: (restype, argtypes)
@@ -66,6 +75,11 @@ _SIGNATURES = {
     'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),
     'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),
     'skgs_assemble_backward': (C.c_int, [_i32] + [_vp] * 16),
+    'skgs_image_loss_workspace_bytes': (C.c_size_t, [_i32, _i32]),
+    'skgs_image_loss': (C.c_int, [_i32, _i32, _vp, _vp, _i32, _i32, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp,
+                                  _vp]),
+    'skgs_adam_step': (C.c_int, [C.POINTER(AdamTensor), _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_float,
+                                 _vp, _vp]),
     'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
 }
 

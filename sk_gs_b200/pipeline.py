@@ -2,7 +2,9 @@
 
 Mirrors what `SkeletonGaussianSplatting.render` does per view in the `sk` stage
 (/root/reference/networks/sk_gs.py:1206-1242 -> forward :1160-1204 -> sk_stage :1109-1150 -> render_gs_offical),
-minus the joint MLP, the loss and the optimizer (out of scope for this path)."""
+minus the joint MLP.  The two steps that follow the path in a training iteration - photometric loss
+(8f-2, networks/sk_gs.py:1524-1529) and Adam (8f-3, networks/gaussian_splatting.py:445-453) - are optional stages of
+`step_grads` / `TrainLoop`; the benchmarked metric (BASELINE.json) excludes them."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -31,7 +33,10 @@ def raster_settings_for(cam: Camera, device, sh_degree: int = 3, scale_modifier:
 class HotPath:
     """Holds the parameters of one synthetic scene on a device and runs the per-view step."""
 
-    def __init__(self, scene: Scene, device='cuda', mode: str = 'W', requires_grad: bool = True):
+    def __init__(self, scene: Scene, device='cuda', mode: str = 'W', requires_grad: bool = True,
+                 merged_sh: bool = False):
+        """`merged_sh`: keep the SH coefficients as ONE [P,16,3] parameter ('shs'; 'f_dc' / 'f_rest' become views of it)
+        instead of the reference's two Parameters that are concatenated on every step (gaussian_splatting.py:155-157)."""
         self.scene = scene
         self.device = torch.device(device)
         self.mode = mode
@@ -39,6 +44,10 @@ class HotPath:
         self.params: Dict[str, Tensor] = {}
         for n in PARAM_NAMES:
             self.params[n] = getattr(scene, n).to(self.device).clone().requires_grad_(requires_grad)
+        if merged_sh:
+            shs = torch.cat((self.params['f_dc'].detach(), self.params['f_rest'].detach()), dim=1)
+            self.params['shs'] = shs.requires_grad_(requires_grad)
+            self.params['f_dc'], self.params['f_rest'] = shs.detach()[:, :1], shs.detach()[:, 1:]
         self.sp_radius = scene.sp_radius.to(self.device).clone().requires_grad_(requires_grad and mode != 'W')
         self.sp_weight = scene.sp_weight.to(self.device).clone().requires_grad_(requires_grad and mode != 'W')
         self.parents = scene.parents.to(self.device)
@@ -54,7 +63,7 @@ class HotPath:
         d_xyz, d_rot, d_scale = out[:3]
         points, scales, rotations, opacity = assemble(p['xyz'], p['scaling'], p['rotation'], p['opacity'], d_xyz,
                                                       d_rot, d_scale)
-        sh = torch.cat((p['f_dc'], p['f_rest']), dim=1)
+        sh = p['shs'] if 'shs' in p else torch.cat((p['f_dc'], p['f_rest']), dim=1)
         return dict(points=points, scales=scales, rotations=rotations, opacity=opacity, sh_features=sh), out
 
     def render(self, view: int = 0):
@@ -74,12 +83,15 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
-    def step_grads(self, view: int, dL_dimage: Tensor, compact_sp_W: bool = False, before_backward=None, arena=None,
-                   after_forward=None, mid_backward=None):
+    def step_grads(self, view: int, dL_dimage: Optional[Tensor], compact_sp_W: bool = False, before_backward=None,
+                   arena=None, after_forward=None, mid_backward=None, target: Optional[Tensor] = None,
+                   loss: Optional[dict] = None):
         """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
         nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
         (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
-        form is cheaper on the host and can be captured into a CUDA graph."""
+        form is cheaper on the host and can be captured into a CUDA graph.
+        With `target` (and `dL_dimage=None`) the upstream gradient comes from the fused L1 + SSIM loss between the rendered
+        image and `target` (`loss` = keyword arguments of losses.image_loss_raw); outputs gain 'loss_terms'."""
         from . import diff_gaussian_rasterization as DGR
         from .fk_lbs import (assemble_backward_raw, assemble_forward_raw, fk_lbs_backward_raw, fk_lbs_forward_raw)
         with torch.no_grad():
@@ -91,12 +103,19 @@ class HotPath:
                 sp_weight=self.sp_weight if self.mode == 'weighted_kernel' else None)
             (points, scales, rotations, opacity), c2 = assemble_forward_raw(p['xyz'], p['scaling'], p['rotation'],
                                                                             p['opacity'], d_xyz, d_rot, d_scale)
-            sh = torch.cat((p['f_dc'], p['f_rest']), dim=1)
+            sh = p['shs'] if 'shs' in p else torch.cat((p['f_dc'], p['f_rest']), dim=1)
             color, depth, alpha, radii, st = DGR.rasterize_forward(self.settings[view], points, opacity, shs=sh,
                                                                    scales=scales, rotations=rotations, quat_wxyz=False)
             join_after = after_forward(radii) if after_forward is not None else None  # e.g. radii MAX on a side stream
             if before_backward is not None:
-                before_backward()  # e.g. join the stream that uploads dL_dimage while the forward runs
+                before_backward()  # e.g. join the stream that uploads dL_dimage / the target while the forward runs
+            loss_terms = None
+            if target is not None:
+                from .losses import image_loss_raw
+                if not hasattr(self, '_loss_buffers'):
+                    self._loss_buffers = {}
+                loss_terms, dL_dimage = image_loss_raw(color, target, out=self._loss_buffers.setdefault(view, {}),
+                                                       **(loss or {}))
             # with an arena (sk_gs_b200.dist.GradArena) every final gradient is written straight into its slot of the
             # flat all-reduce buffer: no packing copies before the exchange
             A = (lambda n: arena.view(n)) if arena is not None else (lambda n: None)
@@ -120,20 +139,22 @@ class HotPath:
         if join_mid is not None:
             join_mid()
         out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
+               'loss_terms': loss_terms,
                'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, p['sk_d_rot'], p['sk_d_scale'], p['g_tr'],
                                                  weights, indices)}
         return out, grads
 
     def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3, compact_sp_W: bool = False,
                      uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None, after_forward=None,
-                     mid_backward=None):
+                     mid_backward=None, target: Optional[Tensor] = None, loss: Optional[dict] = None,
+                     target_host: Optional[Tensor] = None):
         """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
         the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
         in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
         from . import _lib
         from . import diff_gaussian_rasterization as DGR
-        self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward,
-                        mid_backward=mid_backward)
+        kw = dict(arena=arena, after_forward=after_forward, mid_backward=mid_backward, target=target, loss=loss)
+        o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, **kw)
         torch.cuda.synchronize(self.device)
         R = int(DGR.last_header_words(self.device)[0])
         DGR.set_fixed_capacity(int(R * headroom) + 4096)
@@ -141,8 +162,7 @@ class HotPath:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, arena=arena, after_forward=after_forward,
-                                         mid_backward=mid_backward)
+                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, **kw)
                 if epilogue is not None:
                     epilogue(o_, g_)  # e.g. the NCCL gradient exchange: communicators must exist before capture
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -156,15 +176,16 @@ class HotPath:
             join = None
             for dst, src in (uploads or []):
                 dst.copy_(src, non_blocking=True)
-            if dL_host is not None:
+            late = [(d, h) for d, h in ((dL_dimage, dL_host), (target, target_host)) if h is not None]
+            if late:
                 main = torch.cuda.current_stream(self.device)
                 up = torch.cuda.Stream(self.device)
                 up.wait_stream(main)
                 with torch.cuda.stream(up):
-                    dL_dimage.copy_(dL_host, non_blocking=True)
+                    for d, h in late:
+                        d.copy_(h, non_blocking=True)
                 join = lambda: main.wait_stream(up)  # noqa: E731
-            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, arena=arena,
-                                         after_forward=after_forward, mid_backward=mid_backward)
+            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, **kw)
             if epilogue is not None:
                 epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay

@@ -10,6 +10,8 @@ be imported UNMODIFIED from /root/reference.  Functions exercised (all torch, CP
   my_ext/ops_3d/rigid.py                 : quaternion_to_Rt                     -> fk.npz
   networks/sk_gs.py                      : find_root, skeleton_warp, skeleton_warp_v0   -> fk.npz
   my_ext/ops_3d/coord_trans_opencv.py    : perspective                          -> cam.npz
+  networks/losses/ssim.py, image_loss.py : SSIM_Loss, ImageLoss (+ autograd)    -> loss.npz
+  torch.optim.Adam (the reference's optimizer, gaussian_splatting.py:445-453)   -> adam.npz
 """
 import importlib
 import importlib.abc
@@ -130,7 +132,69 @@ def main():
     Tv2c = cv.perspective(fovy=0.6911, n=0.01, f=1000.0, size=(800, 800))
     Tv2c2 = cv.perspective(fovy=0.5, n=0.01, f=1000.0, size=(1920, 1080))
     np.savez(os.path.join(OUT, 'cam.npz'), Tv2c_800=Tv2c.numpy(), Tv2c_1080p=Tv2c2.numpy())
+    make_loss()
+    make_adam()
     print('golden vectors written to', OUT)
+
+
+def make_loss():
+    """The reference's loss modules on random images, fp32 (what the reference runs) and fp64 (tight check of the oracle);
+    the image is [1,H,W,3] as at networks/sk_gs.py:1527, weights of exps/default.yaml:83-84."""
+    ssim_mod = importlib.import_module('networks.losses.ssim')
+    img_mod = importlib.import_module('networks.losses.image_loss')
+    g = torch.Generator().manual_seed(20241017 + 100)
+    out = {}
+    cases = [(37, 45), (64, 80), (11, 9)]
+    for i, (H, W) in enumerate(cases):
+        gt = torch.rand(1, H, W, 3, generator=g)
+        img = (gt + 0.2 * torch.randn(1, H, W, 3, generator=g)).clamp(0, 1) if i != 1 else torch.rand(1, H, W, 3, generator=g)
+        if i == 0:
+            img[0, :4, :5] = gt[0, :4, :5]  # exact zeros of the L1 term
+        for dt, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+            x = img.detach().clone().to(dt).requires_grad_(True)
+            y = gt.to(dt)
+            l1 = img_mod.ImageLoss(method='l1')(x, y)
+            mse = img_mod.ImageLoss(method='mse')(x, y)
+            ss = ssim_mod.SSIM_Loss()(x, y)
+            g_l1, = torch.autograd.grad(l1, x, retain_graph=True)
+            g_mse, = torch.autograd.grad(mse, x, retain_graph=True)
+            g_ss, = torch.autograd.grad(ss, x, retain_graph=True)
+            total = 0.8 * l1 + 0.2 * ss
+            g_total, = torch.autograd.grad(total, x)
+            out.update({f'l1_{tag}_{i}': l1.detach().numpy(), f'mse_{tag}_{i}': mse.detach().numpy(),
+                        f'ssim_{tag}_{i}': ss.detach().numpy(), f'total_{tag}_{i}': total.detach().numpy(),
+                        f'g_l1_{tag}_{i}': g_l1.numpy(), f'g_mse_{tag}_{i}': g_mse.numpy(),
+                        f'g_ssim_{tag}_{i}': g_ss.numpy(), f'g_total_{tag}_{i}': g_total.numpy()})
+        out.update({f'img_{i}': img.numpy(), f'gt_{i}': gt.numpy()})
+    np.savez_compressed(os.path.join(OUT, 'loss.npz'), n=np.int64(len(cases)), **out)
+
+
+def make_adam():
+    """torch.optim.Adam trajectories with the reference's hyper-parameters (exps/default.yaml:121-125) and two param
+    groups with different lr (networks/gaussian_splatting.py:447-452)."""
+    g = torch.Generator().manual_seed(20241017 + 200)
+    shapes = [(301, 3), (77, 16), (5000,)]
+    lrs = [1.6e-4, 2.5e-3, 5e-2]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    opt = torch.optim.Adam([{'params': [p], 'lr': lr} for p, lr in zip(params, lrs)], lr=1e-3, eps=1e-15,
+                           betas=(0.9, 0.999))
+    out = {f'p0_{i}': p.detach().clone().numpy() for i, p in enumerate(params)}
+    steps = 4
+    for t in range(steps):
+        for i, p in enumerate(params):
+            scale = 10.0 ** (-2 * i)
+            p.grad = torch.randn(*shapes[i], generator=g) * scale
+            if t == 2 and i == 0:
+                p.grad[::3] = 0  # rows without gradient still move (momentum)
+            out[f'g{t}_{i}'] = p.grad.clone().numpy()
+        opt.step()
+        for i, p in enumerate(params):
+            st = opt.state[p]
+            out[f'p{t + 1}_{i}'] = p.detach().clone().numpy()
+            out[f'm{t + 1}_{i}'] = st['exp_avg'].clone().numpy()
+            out[f'v{t + 1}_{i}'] = st['exp_avg_sq'].clone().numpy()
+    np.savez_compressed(os.path.join(OUT, 'adam.npz'), steps=np.int64(steps), n=np.int64(len(shapes)),
+                        lrs=np.array(lrs), **out)
 
 
 if __name__ == '__main__':

@@ -15,5 +15,9 @@ for line in sys.stdin:
         print(f"  {k:26s} {v['us_per_step']:9.1f} us/step  x{v['launches_per_step']:<4} {v['algorithmic_GBps']:8.1f} GB/s  {v['frac_of_peak']:.3f}")
     if tot:
         print(f"  {'sum of kernels':26s} {tot:9.1f} us/step")
+    if d.get('full_iteration'):
+        print('full_iteration:', d['full_iteration'])
+    if d.get('render_fps'):
+        print('render_fps:', d['render_fps']['value'])
     if d.get('cpu_baseline'):
         print('cpu_baseline:', d['cpu_baseline']['value'], d['cpu_baseline']['unit'], 'cores', d['cpu_baseline']['cores'], d['cpu_baseline']['kind'])
