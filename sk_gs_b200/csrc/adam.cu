@@ -14,7 +14,13 @@ namespace {
 
 constexpr int AD_THREADS = 256;
 constexpr int AD_VEC = 4;
-constexpr int AD_ILP = 4;
+#ifndef SKGS_AD_ILP
+#define SKGS_AD_ILP 2
+#endif
+#ifndef SKGS_AD_MINB
+#define SKGS_AD_MINB 4
+#endif
+constexpr int AD_ILP = SKGS_AD_ILP;
 constexpr int AD_CHUNK = AD_THREADS * AD_VEC * AD_ILP;  // parameters per CTA
 
 struct AdamArgs {
@@ -33,67 +39,87 @@ struct AdamArgs {
   float grad_scale;
 };
 
-__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamArgs& a, float step_size,
-                                            float bc2_sqrt) {
+struct Hyper {
+  float w1, beta2, w2, inv_bc2_sqrt, eps, step_size, step_size2;
+  uint32_t period, split;
+  __device__ __forceinline__ float ss(uint32_t phase) const {  // phase = element index mod period
+    return period != 0 && phase >= split ? step_size2 : step_size;
+  }
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const Hyper& h, float step_size) {
   // same operation order as torch's foreach implementation (lerp, mul + addcmul, sqrt / div / add, addcdiv)
-  m = m + a.w1 * (g - m);
-  v = v * a.beta2 + (a.w2 * g) * g;
-  const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+  m = m + h.w1 * (g - m);
+  v = v * h.beta2 + (h.w2 * g) * g;
+  const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;  // torch divides by bc2_sqrt: equal to 1 ulp
   p = p + (-step_size) * (m / denom);
 }
 
-__global__ void __launch_bounds__(AD_THREADS) adam_kernel(const __grid_constant__ AdamArgs a) {
-  int ti = 0;
-  while (ti + 1 < a.count && (int)blockIdx.x >= a.block_start[ti + 1]) ++ti;
-  const skgs_adam_tensor& T = a.t[ti];
-  const float step_size = a.dyn ? __ldg(a.dyn + 1 + 2 * a.slot[ti]) : a.step_size[ti];
-  const float step_size2 = a.dyn ? __ldg(a.dyn + 2 + 2 * a.slot[ti]) : a.step_size2[ti];
-  const int period = T.period, split = T.split;
-  auto ss = [&](int64_t i) { return period > 0 && (int)(i % period) >= split ? step_size2 : step_size; };
-  const float bc2_sqrt = a.dyn ? __ldg(a.dyn) : a.bc2_sqrt;
-  const int64_t base = (int64_t)(blockIdx.x - a.block_start[ti]) * AD_CHUNK;
-  const int64_t end = min(T.numel, base + AD_CHUNK);
+// gradient of element (row, col) of the skinning table from its compact [rows, K] form
+__device__ __forceinline__ float knn_grad(const skgs_adam_tensor& T, int64_t row, int col) {
+  const int64_t* __restrict__ idx = T.knn_indices + row * T.K;
+  const float* __restrict__ gk = T.grad + row * T.K;
+  float g = 0.f;
+  for (int k = 0; k < T.K; ++k) g += ((int)__ldg(idx + k) == col) ? __ldg(gk + k) : 0.f;
+  return g;
+}
 
-  if (T.knn_indices) {
-    for (int64_t i = base + threadIdx.x; i < end; i += AD_THREADS) {
-      const int64_t row = i / T.cols;
-      const int col = (int)(i - row * T.cols);
-      float g = 0.f;
-      for (int k = 0; k < T.K; ++k)
-        if ((int)T.knn_indices[row * T.K + k] == col) g += T.grad[row * T.K + k];
-      g *= a.grad_scale;
-      float p = T.param[i], m = T.exp_avg[i], v = T.exp_avg_sq[i];
-      adam_update(p, g, m, v, a, ss(i), bc2_sqrt);
-      T.param[i] = p;
-      T.exp_avg[i] = m;
-      T.exp_avg_sq[i] = v;
-    }
-    return;
-  }
-
-  const bool vec_ok =
-      ((((uintptr_t)T.param) | ((uintptr_t)T.grad) | ((uintptr_t)T.exp_avg) | ((uintptr_t)T.exp_avg_sq)) & 15) == 0;
-  if (vec_ok && end - base == AD_CHUNK) {
+// All loads of a thread's AD_ILP x 4 parameters are issued before the first dependent instruction: the kernel is a pure
+// stream (28 B per parameter) and lives on memory-level parallelism.
+template <bool KNN>
+__device__ __forceinline__ void adam_chunk(const skgs_adam_tensor& T, const Hyper& h, float grad_scale, int64_t base,
+                                           int64_t end) {
+  const bool vec_ok = ((((uintptr_t)T.param) | ((uintptr_t)T.exp_avg) | ((uintptr_t)T.exp_avg_sq) |
+                        (KNN ? (uintptr_t)0 : (uintptr_t)T.grad)) & 15) == 0;
+  if (vec_ok && end - base == AD_CHUNK && (!KNN || (T.cols & 3) == 0)) {
     float4 p[AD_ILP], g[AD_ILP], m[AD_ILP], v[AD_ILP];
+    uint32_t phase[AD_ILP];
 #pragma unroll
     for (int u = 0; u < AD_ILP; ++u) {
-      const int64_t i = base + ((int64_t)u * AD_THREADS + threadIdx.x) * AD_VEC;
+      const int64_t i = base + (u * AD_THREADS + threadIdx.x) * AD_VEC;
       p[u] = *(const float4*)(T.param + i);
-      g[u] = __ldg((const float4*)(T.grad + i));
       m[u] = *(const float4*)(T.exp_avg + i);
       v[u] = *(const float4*)(T.exp_avg_sq + i);
+      if (!KNN) g[u] = __ldg((const float4*)(T.grad + i));
     }
 #pragma unroll
     for (int u = 0; u < AD_ILP; ++u) {
-      const int64_t i = base + ((int64_t)u * AD_THREADS + threadIdx.x) * AD_VEC;
-      adam_update(p[u].x, g[u].x * a.grad_scale, m[u].x, v[u].x, a, ss(i), bc2_sqrt);
-      adam_update(p[u].y, g[u].y * a.grad_scale, m[u].y, v[u].y, a, ss(i + 1), bc2_sqrt);
-      adam_update(p[u].z, g[u].z * a.grad_scale, m[u].z, v[u].z, a, ss(i + 2), bc2_sqrt);
-      adam_update(p[u].w, g[u].w * a.grad_scale, m[u].w, v[u].w, a, ss(i + 3), bc2_sqrt);
+      const int64_t i = base + (u * AD_THREADS + threadIdx.x) * AD_VEC;
+      phase[u] = h.period ? (uint32_t)(i % h.period) : 0u;
+      if (KNN) {
+        // cols % 4 == 0 here (checked by the caller of this path): the four parameters share one row, so the row's K
+        // (index, gradient) pairs are read once and routed to the lane they belong to
+        const int64_t row = (T.numel >> 31) == 0 ? (int64_t)((uint32_t)i / (uint32_t)T.cols) : i / T.cols;
+        const int col = (int)(i - row * T.cols);
+        const int* __restrict__ idx = (const int*)(T.knn_indices + row * T.K);  // low words (little endian, < 2^31)
+        const float* __restrict__ gk = T.grad + row * T.K;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        for (int k = 0; k < T.K; ++k) {
+          const int d = __ldg(idx + 2 * k) - col;
+          const float gv = __ldg(gk + k);
+          g0 += d == 0 ? gv : 0.f;
+          g1 += d == 1 ? gv : 0.f;
+          g2 += d == 2 ? gv : 0.f;
+          g3 += d == 3 ? gv : 0.f;
+        }
+        g[u] = make_float4(g0, g1, g2, g3);
+      }
     }
 #pragma unroll
     for (int u = 0; u < AD_ILP; ++u) {
-      const int64_t i = base + ((int64_t)u * AD_THREADS + threadIdx.x) * AD_VEC;
+      const uint32_t ph = phase[u], per = h.period;
+      auto wrap = [&](uint32_t x) {
+        while (per != 0 && x >= per) x -= per;
+        return x;
+      };
+      adam_update(p[u].x, g[u].x * grad_scale, m[u].x, v[u].x, h, h.ss(ph));
+      adam_update(p[u].y, g[u].y * grad_scale, m[u].y, v[u].y, h, h.ss(wrap(ph + 1)));
+      adam_update(p[u].z, g[u].z * grad_scale, m[u].z, v[u].z, h, h.ss(wrap(ph + 2)));
+      adam_update(p[u].w, g[u].w * grad_scale, m[u].w, v[u].w, h, h.ss(wrap(ph + 3)));
+    }
+#pragma unroll
+    for (int u = 0; u < AD_ILP; ++u) {
+      const int64_t i = base + (u * AD_THREADS + threadIdx.x) * AD_VEC;
       *(float4*)(T.param + i) = p[u];
       *(float4*)(T.exp_avg + i) = m[u];
       *(float4*)(T.exp_avg_sq + i) = v[u];
@@ -101,12 +127,41 @@ __global__ void __launch_bounds__(AD_THREADS) adam_kernel(const __grid_constant_
     return;
   }
   for (int64_t i = base + threadIdx.x; i < end; i += AD_THREADS) {
+    float g;
+    if (KNN) {
+      const int64_t row = i / T.cols;
+      g = knn_grad(T, row, (int)(i - row * T.cols));
+    } else {
+      g = T.grad[i];
+    }
     float p = T.param[i], m = T.exp_avg[i], v = T.exp_avg_sq[i];
-    adam_update(p, T.grad[i] * a.grad_scale, m, v, a, ss(i), bc2_sqrt);
+    adam_update(p, g * grad_scale, m, v, h, h.ss(h.period ? (uint32_t)(i % h.period) : 0u));
     T.param[i] = p;
     T.exp_avg[i] = m;
     T.exp_avg_sq[i] = v;
   }
+}
+
+__global__ void __launch_bounds__(AD_THREADS, SKGS_AD_MINB) adam_kernel(const __grid_constant__ AdamArgs a) {
+  int ti = 0;
+  while (ti + 1 < a.count && (int)blockIdx.x >= a.block_start[ti + 1]) ++ti;
+  const skgs_adam_tensor& T = a.t[ti];
+  Hyper h;
+  h.w1 = a.w1;
+  h.beta2 = a.beta2;
+  h.w2 = a.w2;
+  h.eps = a.eps;
+  h.inv_bc2_sqrt = 1.f / (a.dyn ? __ldg(a.dyn) : a.bc2_sqrt);
+  h.step_size = a.dyn ? __ldg(a.dyn + 1 + 2 * a.slot[ti]) : a.step_size[ti];
+  h.step_size2 = a.dyn ? __ldg(a.dyn + 2 + 2 * a.slot[ti]) : a.step_size2[ti];
+  h.period = (uint32_t)T.period;
+  h.split = (uint32_t)T.split;
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[ti]) * AD_CHUNK;
+  const int64_t end = min(T.numel, base + AD_CHUNK);
+  if (T.knn_indices)
+    adam_chunk<true>(T, h, a.grad_scale, base, end);
+  else
+    adam_chunk<false>(T, h, a.grad_scale, base, end);
 }
 
 }  // namespace

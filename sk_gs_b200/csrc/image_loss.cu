@@ -7,8 +7,8 @@
 // convolutions, C1 = 0.01^2, C2 = 0.03^2), :39-41 (1 - mean), weights exps/default.yaml:83-84 (0.8 / 0.2),
 // call site networks/sk_gs.py:1524-1529.  The reference runs 5 conv2d + ~20 element-wise kernels forward and the
 // autograd mirror backward; here
-//   ssim_stats_kernel : window statistics by a separable convolution in shared memory, SSIM map, both loss sums, and
-//                       the three partial-derivative maps dS/dmu1, dS/dE[xx], dS/dE[xy];
+//   ssim_stats_kernel : window statistics (mu1, mu2, E[xx+yy], E[xy]) by a separable convolution in shared memory,
+//                       SSIM map, both loss sums, and the three partial-derivative maps dS/dmu1, dS/dE[xx], dS/dE[xy];
 //   ssim_grad_kernel  : the adjoint (same symmetric window) convolution of those maps -> dL/dI, and the loss scalars.
 // The rendered image arrives channel-major [3,H,W] (what composite_fwd_kernel writes); the target may be channel-major
 // or pixel-major [H,W,3|4] (datasets hand out HWC / RGBA, sk_gs.py:1525).
@@ -24,6 +24,7 @@ constexpr int LH = LT + 2 * LR;  // tile + halo
 constexpr int LS = 8;            // outputs per thread in the horizontal pass
 constexpr int LV = 4;            // outputs per thread in the vertical pass
 constexpr int L_THREADS = 256;
+constexpr int L_LOADS = (LH * LH + L_THREADS - 1) / L_THREADS;  // tile + halo elements per thread
 static_assert(LT * LT == L_THREADS * LV, "vertical pass covers the tile");
 static_assert(LH * (LT / LS) <= L_THREADS, "horizontal pass fits one round");
 
@@ -56,45 +57,60 @@ __global__ void __launch_bounds__(L_THREADS)
                       int mse, Window win, float* __restrict__ dmaps, double* __restrict__ sums) {
   __shared__ float sX[LH][LH + 1];
   __shared__ float sY[LH][LH + 1];
-  __shared__ float sHz[5][LH][LT + 1];
+  __shared__ float sHz[4][LH][LT + 1];
   __shared__ float sRed[2][L_THREADS / 32];
   const int tid = threadIdx.x;
   const int c = blockIdx.z;
   const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
 
-  for (int i = tid; i < LH * LH; i += L_THREADS) {
-    const int r = i / LH, col = i - r * LH;
-    const int gy = y0 + r - LR, gx = x0 + col - LR;
-    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;  // zero padding (F.conv2d padding=5, ssim.py:47)
-    sX[r][col] = in ? img[((size_t)c * H + gy) * W + gx] : 0.f;
-    sY[r][col] = in ? target_at(tgt, tgt_pix_stride, c, gy, gx, H, W) : 0.f;
+  // all global loads of the thread are issued before the first shared-memory store (the tile load is pure latency)
+  {
+    float rx[L_LOADS], ry[L_LOADS];
+#pragma unroll
+    for (int it = 0; it < L_LOADS; ++it) {
+      const int i = tid + it * L_THREADS;
+      const int r = i / LH, col = i - r * LH;
+      const int gy = y0 + r - LR, gx = x0 + col - LR;
+      const bool in = i < LH * LH && gy >= 0 && gy < H && gx >= 0 && gx < W;  // zero padding (F.conv2d padding=5, ssim.py:47)
+      rx[it] = in ? img[((size_t)c * H + gy) * W + gx] : 0.f;
+      ry[it] = in ? target_at(tgt, tgt_pix_stride, c, gy, gx, H, W) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < L_LOADS; ++it) {
+      const int i = tid + it * L_THREADS;
+      if (i < LH * LH) {
+        const int r = i / LH, col = i - r * LH;
+        sX[r][col] = rx[it];
+        sY[r][col] = ry[it];
+      }
+    }
   }
   __syncthreads();
 
   if (tid < LH * (LT / LS)) {
     const int r = tid / (LT / LS), s = (tid % (LT / LS)) * LS;
-    float v[5][LS + LW - 1], o[5][LS];
+    // four maps, not five: sigma1^2 and sigma2^2 only ever appear as their sum, so x^2 + y^2 is filtered once
+    float v[4][LS + LW - 1], o[4][LS];
 #pragma unroll
     for (int k = 0; k < LS + LW - 1; ++k) {
       const float a = sX[r][s + k], b = sY[r][s + k];
       v[0][k] = a;
       v[1][k] = b;
-      v[2][k] = a * a;
-      v[3][k] = b * b;
-      v[4][k] = a * b;
+      v[2][k] = fmaf(a, a, b * b);
+      v[3][k] = a * b;
     }
-    hpass<5>(win, v, o);
+    hpass<4>(win, v, o);
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int j = 0; j < LS; ++j) sHz[q][r][s + j] = o[q][j];
   }
   __syncthreads();
 
   const int col = tid & 31, r0 = (tid >> 5) * LV;
-  float st[5][LV];
+  float st[4][LV];
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float v[LV + LW - 1];
 #pragma unroll
     for (int k = 0; k < LV + LW - 1; ++k) v[k] = sHz[q][r0 + k][col];
@@ -116,9 +132,9 @@ __global__ void __launch_bounds__(L_THREADS)
     if (gy < H && gx < W) {
       const float mu1 = st[0][j], mu2 = st[1][j];
       const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-      const float s1 = st[2][j] - mu1_sq, s2 = st[3][j] - mu2_sq, s12 = st[4][j] - mu12;
+      const float s12 = st[3][j] - mu12;
       const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
-      const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+      const float B1 = mu1_sq + mu2_sq + C1, B2 = (st[2][j] - mu1_sq - mu2_sq) + C2;  // sigma1^2 + sigma2^2 + C2
       const float iB1 = 1.f / B1, iB2 = 1.f / B2;
       const float S = A1 * A2 * iB1 * iB2;  // ssim.py:61
       sum_ssim += S;
@@ -172,13 +188,27 @@ __global__ void __launch_bounds__(L_THREADS)
   const size_t n = (size_t)3 * H * W;
   if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && tid == 0) write_terms(sums, (double)n, w_img, w_ssim, terms);
 
-  for (int i = tid; i < LH * LH; i += L_THREADS) {
-    const int r = i / LH, col = i - r * LH;
-    const int gy = y0 + r - LR, gx = x0 + col - LR;
-    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;  // the adjoint only sums over pixels that exist
-    const size_t at = in ? ((size_t)c * H + gy) * W + gx : 0;
+  {
+    float rd[3][L_LOADS];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) sD[q][r][col] = in ? dmaps[q * n + at] : 0.f;
+    for (int it = 0; it < L_LOADS; ++it) {
+      const int i = tid + it * L_THREADS;
+      const int r = i / LH, col = i - r * LH;
+      const int gy = y0 + r - LR, gx = x0 + col - LR;
+      const bool in = i < LH * LH && gy >= 0 && gy < H && gx >= 0 && gx < W;  // the adjoint only sums over pixels that exist
+      const size_t at = in ? ((size_t)c * H + gy) * W + gx : 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) rd[q][it] = in ? dmaps[q * n + at] : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < L_LOADS; ++it) {
+      const int i = tid + it * L_THREADS;
+      if (i < LH * LH) {
+        const int r = i / LH, col = i - r * LH;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) sD[q][r][col] = rd[q][it];
+      }
+    }
   }
   __syncthreads();
 

@@ -11,6 +11,9 @@ VARIANTS = {
     'rslots4': ['-DSKGS_RSLOTS=4'],
     'os8': ['-DSKGS_OS_ITEMS=8'],
     'os24': ['-DSKGS_OS_ITEMS=24'],
+    'adilp4': ['-DSKGS_AD_ILP=4', '-DSKGS_AD_MINB=2'],
+    'adilp1': ['-DSKGS_AD_ILP=1', '-DSKGS_AD_MINB=8'],
+    'adilp2b8': ['-DSKGS_AD_ILP=2', '-DSKGS_AD_MINB=6'],
 }
 out_dir = os.path.join(ROOT, 'sk_gs_b200', 'variants')
 os.makedirs(out_dir, exist_ok=True)
