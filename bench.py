@@ -124,7 +124,9 @@ def run_ours(args, world, rank, local):
     torch.cuda.set_device(dev)
     cfg = S.CONFIGS[args.workload]
     sc = S.make_scene(cfg, views=max(world, 1))
-    hp = HotPath(sc, dev, mode='W')
+    # SH coefficients live as one [P,16,3] parameter (what the rasterizer reads and what skgs_adam_step updates with two
+    # learning rates); the reference keeps f_dc / f_rest apart and concatenates them on every step
+    hp = HotPath(sc, dev, mode='W', merged_sh=not args.autograd)
     view = rank % len(sc.cameras)
     H, W = cfg.H, cfg.W
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -363,6 +365,7 @@ def run_ours(args, world, rank, local):
                                f'K=5 LBS mode W, fwd+bwd', 'num_rendered': R, 'views_per_step': world,
                    'parallelism': f'view-sharded dp{world}' + (f' + {exchange_kind}' if world > 1 else ''),
                    'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs',
+                   'sh_layout': 'f_dc/f_rest parameters + cat per step' if args.autograd else 'one [P,16,3] parameter',
                    'launch': 'CUDA graph replay (fixed binning capacity, overflow flag checked)' if args.graph
                    else ('eager launches through the autograd API' if args.autograd else 'eager launches')},
         'clocks': clocks,
