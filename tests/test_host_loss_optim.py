@@ -1,0 +1,89 @@
+"""Host-side logic of the loss / optimizer mirrors that needs no GPU: layout detection, hyper-parameter tables, param
+group handling, and the 'no CPU fallback' rule (CPU tensors must raise, never silently compute)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from sk_gs_b200 import _lib
+from sk_gs_b200 import losses as LS
+from sk_gs_b200.optim import Adam, adam_hyper, adam_step_raw
+
+
+def test_target_layout_detection():
+    chw = torch.rand(3, 10, 12)
+    t, s = LS._target(chw)
+    assert s == 0 and t.data_ptr() == chw.data_ptr()
+    hwc = torch.rand(10, 12, 3)
+    t, s = LS._target(hwc)
+    assert s == 3 and t.data_ptr() == hwc.data_ptr()
+    rgba = torch.rand(10, 12, 4)
+    t, s = LS._target(rgba[..., :3])  # what sk_gs.py:1525 hands over: read in place with pixel stride 4
+    assert s == 4 and t.data_ptr() == rgba.data_ptr()
+    t, s = LS._target(rgba)
+    assert s == 4
+    t, s = LS._target(hwc[None])
+    assert s == 3 and t.shape == (10, 12, 3)
+    t, s = LS._target(hwc.double())
+    assert s == 3 and t.dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        LS._target(torch.rand(10, 12, 5))
+    with pytest.raises(RuntimeError):
+        LS._target(torch.rand(10, 12))
+
+
+def test_image_layout_detection():
+    chw = torch.rand(3, 8, 9)
+    assert LS._as_chw(chw).data_ptr() == chw.data_ptr()
+    hwc_view = chw.permute(1, 2, 0)  # the rasterizer output permuted to HWC (sk_gs.py:1229): maps back without a copy
+    assert LS._as_chw(hwc_view).data_ptr() == chw.data_ptr()
+    assert LS._as_chw(hwc_view[None]).data_ptr() == chw.data_ptr()
+    assert LS._as_chw(torch.rand(8, 9, 3)).shape == (3, 8, 9)
+    with pytest.raises(RuntimeError):
+        LS._as_chw(torch.rand(2, 3, 8, 9))
+    with pytest.raises(RuntimeError):
+        LS._as_chw(torch.rand(8, 9, 2))
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        LS.image_loss_raw(torch.rand(3, 8, 8), torch.rand(3, 8, 8))
+    z = torch.zeros(8)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        adam_step_raw([z], [z], [z], [z], [1e-3], 1)
+    with pytest.raises(RuntimeError):
+        adam_step_raw([z], [z, z], [z], [z], [1e-3], 1)
+    with pytest.raises(ValueError):
+        LS.ImageLoss(method='huber')
+    with pytest.raises(NotImplementedError):
+        LS.SSIM_Loss(window_size=7)
+
+
+def test_adam_hyper_table():
+    h = adam_hyper([1e-3, (2e-3, 1e-4, 48, 3)], step=3)
+    bc1, bc2 = 1 - 0.9 ** 3, 1 - 0.999 ** 3
+    assert len(h) == 5
+    assert h[0] == pytest.approx(bc2 ** 0.5) and h[1] == h[2] == pytest.approx(1e-3 / bc1)
+    assert h[3] == pytest.approx(2e-3 / bc1) and h[4] == pytest.approx(1e-4 / bc1)
+
+
+def test_adam_param_groups_like_torch():
+    a, b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2))
+    opt = Adam([{'params': [a], 'lr': 0.1, 'name': 'xyz'}, {'params': b}], lr=1e-3, eps=1e-15)
+    assert [g['lr'] for g in opt.param_groups] == [0.1, 1e-3]
+    assert opt.param_groups[0]['name'] == 'xyz' and opt.param_groups[1]['eps'] == 1e-15
+    assert opt.param_groups[1]['params'] == [b]
+    opt.param_groups[0]['lr'] = 0.05  # schedulers write here (gaussian_splatting.py:466-471)
+    opt.step()  # no gradients yet: nothing to do, no library call
+    assert opt.state == {}
+    a.grad = torch.ones(3)
+    opt.zero_grad()
+    assert a.grad is None
+    with pytest.raises(ValueError):
+        Adam([])
+
+
+def test_adam_tensor_struct_matches_header():
+    # struct skgs_adam_tensor (include/skgs_b200.h): 4 pointers, int64, 2 doubles, 4 int32, pointer
+    assert C.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 16 + 16 + 8
+    assert _lib.AdamTensor.knn_indices.offset == 72 and _lib.AdamTensor.period.offset == 56
