@@ -344,7 +344,7 @@ def run_ours(args, world, rank, local):
     # ---- widening rows: the complete iteration render -> L1+SSIM loss -> backward -> Adam as one
     # CUDA graph.  Extra information only; the headline metric above is BASELINE.json's (loss and optimizer excluded).
     iteration = None
-    if rank == 0 and not args.no_iteration:
+    if rank == 0 and world == 1 and not args.no_iteration:
         try:
             iteration = full_iteration(args, sc, cfg, dev, view, flush, kern)
         except Exception as e:  # noqa: never let the extra section take the contract line down

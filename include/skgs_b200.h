@@ -279,6 +279,38 @@ SKGS_API int skgs_adam_step(const skgs_adam_tensor* tensors /* host */, int32_t 
                             double beta2, double eps, float grad_scale, const float* dynamic_hyper,
                             void* stream);
 
+/* Joint-rotation network of the `sk` stage, the step before forward kinematics:
+ * joints [M,3], time t -> sk_r [M,4] (unit quaternion xyzw), d_rot [M,4], d_scale [M,3].
+ * Replaces SimpleDeformationNetwork.forward (networks/sk_gs.py:134-164: freq encoders freqencoder.cu:7-31, MLP_with_skips
+ * my_ext/blocks/mlp.py:44-85) plus the head of `kinematic` (sk_gs.py:1074-1076) and their autograd.
+ * Parameters live in ONE flat array `theta`: for hidden layer i = 0..depth-1 the Linear weight [width, in_i] (row-major,
+ * torch layout) then its bias [width]; then the three heads as one [11, in] weight and [11] bias
+ * (rows 0-3 rotation, 4-7 d_rot, 8-10 d_scale).  in_0 = enc = 3 (1 + 2 degree_p) + (1 + 2 degree_t); in_i = width
+ * (+ enc if bit i-1 of skip_mask is set: the encoded input is concatenated AFTER the ReLU of layer i-1).
+ * `t` is a DEVICE pointer to one float (so that a captured graph can be replayed with a new time).
+ * The backward uses the activations the forward left in `workspace` (same pointer, no call in between) and ASSIGNS
+ * dL_dtheta [param_count] and dL_djoints [M,3] (the part that flows through the network input; may be NULL). */
+typedef struct skgs_joint_mlp {
+  int32_t M;
+  int32_t degree_p;      /* 10 (exps/default.yaml:50) */
+  int32_t degree_t;      /* 6  (exps/default.yaml:52) */
+  int32_t width;         /* 256 */
+  int32_t depth;         /* 8 */
+  int32_t skip_mask;     /* skips [4] -> 1 << 4 */
+  int32_t n_out;         /* 11 */
+  int32_t rotation_head; /* 1: sk_r = normalize(out[0:4] + (0,0,0,1)), F.normalize eps 1e-12; 0: raw outputs */
+  const float* theta;
+} skgs_joint_mlp;
+SKGS_API int skgs_joint_mlp_layout(const skgs_joint_mlp* net, int64_t* weight_offsets /* [depth+1] */,
+                                   int64_t* bias_offsets /* [depth+1] */, int32_t* in_dims /* [depth+1] */,
+                                   int64_t* param_count);
+SKGS_API size_t skgs_joint_mlp_workspace_bytes(const skgs_joint_mlp* net);
+SKGS_API int skgs_joint_mlp_forward(const skgs_joint_mlp* net, const float* joints, const float* t, float* sk_r,
+                                    float* d_rot, float* d_scale, void* workspace, void* stream);
+SKGS_API int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, const float* dL_dd_rot,
+                                     const float* dL_dd_scale, float* dL_dtheta, float* dL_djoints, void* workspace,
+                                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange
  * ------------------------------------------------------------------------------------------------------------- */

@@ -51,6 +51,13 @@ class AdamTensor(C.Structure):
     ]
 
 
+class JointMlp(C.Structure):
+    _fields_ = [
+        ('M', C.c_int32), ('degree_p', C.c_int32), ('degree_t', C.c_int32), ('width', C.c_int32), ('depth', C.c_int32),
+        ('skip_mask', C.c_int32), ('n_out', C.c_int32), ('rotation_head', C.c_int32), ('theta', C.c_void_p),
+    ]
+
+
 ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
 
@@ -80,6 +87,11 @@ _SIGNATURES = {
                                   _vp]),
     'skgs_adam_step': (C.c_int, [C.POINTER(AdamTensor), _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_float,
                                  _vp, _vp]),
+    'skgs_joint_mlp_layout': (C.c_int, [C.POINTER(JointMlp), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    'skgs_joint_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(JointMlp)]),
+    'skgs_joint_mlp_forward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
+    'skgs_joint_mlp_backward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
 }
 

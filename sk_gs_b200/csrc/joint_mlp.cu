@@ -1,0 +1,444 @@
+// joint_mlp.cu - the joint-rotation network of the `sk` stage, forward and backward: the step BEFORE
+// forward kinematics.  joints [M,3], time t  ->  per-joint rotation quaternion sk_r [M,4], d_rot [M,4], d_scale [M,3].
+//
+// Reference: SimpleDeformationNetwork networks/sk_gs.py:134-164 (frequency encoders of position and time, concatenation,
+// MLP), MLP_with_skips my_ext/blocks/mlp.py:44-85 (ReLU after every hidden layer; a skip layer concatenates the encoded
+// input AFTER its ReLU; one Linear per head), frequency encoder my_ext/_C/src/nerf/freqencoder.cu:7-31 / :36-62, the
+// head sk_r = normalize(out + (0,0,0,1)) networks/sk_gs.py:1075-1076; configuration exps/default.yaml:48-55.
+// The reference runs this as ~30 torch/cuBLAS launches forward and ~60 backward on M <= 64 rows - pure launch latency.
+//
+// Round-1 form: M is tiny, so every matrix product is one launch of a small strided fp32 GEMM (`small_gemm_kernel`,
+// exact FFMA chains, no tensor cores: results must match the reference's fp32 Linear layers) with bias, ReLU, ReLU-mask,
+// skip-concatenation and bias-gradient fused in; 11 launches forward, 21 backward, all capturable in the step's CUDA
+// graph.  (Next: one thread-block cluster with the activations in distributed shared memory.)
+#include <cstring>
+
+#include "common.cuh"
+
+namespace skgs {
+namespace {
+
+constexpr int GM_TI = 32;                    // rows of C per CTA: one per lane
+constexpr int GM_WARPS = 4;
+constexpr int GM_JW = 2;                     // columns of C per warp
+constexpr int GM_TJ = GM_WARPS * GM_JW;      // columns of C per CTA
+constexpr int GM_RC = 64;                    // reduction chunk staged in shared memory
+constexpr int GM_LD = GM_RC + 4;             // row stride: 16-byte aligned rows, conflict-free 128-bit loads
+constexpr int GM_THREADS = GM_WARPS * 32;
+constexpr int MAX_X0_USERS = 8;
+
+// C(i,j) = epilogue( sum_r A(i,r) * B(j,r) ),  i < I, j < J, r < R; every operand is addressed through element strides.
+struct GemmOp {
+  int I, J, R;
+  const float* A;  long long a_si, a_sr;
+  const float* A2; long long a2_si, a2_sr; int r_split;  // r >= r_split reads A2(i, r - r_split)  (skip concatenation)
+  const float* B;  long long b_sj, b_sr;
+  const float* B2; long long b2_sj, b2_sr; int j_split;  // j >= j_split reads B2(j - j_split, r)
+  int ones_col;                                           // B(ones_col, r) = 1: column sums of A (bias gradient)
+  float* C; long long c_si, c_sj;
+  float* C_ones;                                          // where column `ones_col` of C goes (contiguous in i)
+  const float* bias;                                      // + bias[j]
+  int relu;                                               // max(., 0)
+  const float* mask; long long m_si, m_sj;                // * (mask(i,j) > 0): ReLU backward
+};
+
+__device__ __forceinline__ float gemm_a(const GemmOp& op, int i, int r) {
+  if (i >= op.I || r >= op.R) return 0.f;
+  return r < op.r_split ? op.A[i * op.a_si + r * op.a_sr] : op.A2[i * op.a2_si + (r - op.r_split) * op.a2_sr];
+}
+
+__device__ __forceinline__ float gemm_b(const GemmOp& op, int j, int r) {
+  if (j >= op.J || r >= op.R) return 0.f;
+  if (j == op.ones_col) return 1.f;
+  return j < op.j_split ? op.B[j * op.b_sj + r * op.b_sr] : op.B2[(j - op.j_split) * op.b2_sj + r * op.b2_sr];
+}
+
+__global__ void __launch_bounds__(GM_THREADS) small_gemm_kernel(const __grid_constant__ GemmOp op) {
+  __shared__ __align__(16) float As[GM_TI][GM_LD];
+  __shared__ __align__(16) float Bs[GM_TJ][GM_LD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * GM_TI, j0 = blockIdx.y * GM_TJ;
+  const bool a_fast_r = op.a_sr == 1, b_fast_r = op.b_sr == 1;  // walk the contiguous direction with consecutive threads
+  float acc[GM_JW];
+#pragma unroll
+  for (int jj = 0; jj < GM_JW; ++jj) acc[jj] = 0.f;
+
+  for (int r0 = 0; r0 < op.R; r0 += GM_RC) {
+    for (int e = tid; e < GM_TI * GM_RC; e += GM_THREADS) {
+      const int ii = a_fast_r ? e / GM_RC : e % GM_TI, rr = a_fast_r ? e % GM_RC : e / GM_TI;
+      As[ii][rr] = gemm_a(op, i0 + ii, r0 + rr);
+    }
+    for (int e = tid; e < GM_TJ * GM_RC; e += GM_THREADS) {
+      const int jj = b_fast_r ? e / GM_RC : e % GM_TJ, rr = b_fast_r ? e % GM_RC : e / GM_TJ;
+      Bs[jj][rr] = gemm_b(op, j0 + jj, r0 + rr);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < GM_RC; rr += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[lane][rr]);
+#pragma unroll
+      for (int jj = 0; jj < GM_JW; ++jj) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[warp * GM_JW + jj][rr]);
+        acc[jj] = fmaf(a.x, b.x, acc[jj]);
+        acc[jj] = fmaf(a.y, b.y, acc[jj]);
+        acc[jj] = fmaf(a.z, b.z, acc[jj]);
+        acc[jj] = fmaf(a.w, b.w, acc[jj]);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int i = i0 + lane;
+  if (i >= op.I) return;
+#pragma unroll
+  for (int jj = 0; jj < GM_JW; ++jj) {
+    const int j = j0 + warp * GM_JW + jj;
+    if (j >= op.J) continue;
+    float v = acc[jj];
+    if (j == op.ones_col) {
+      op.C_ones[i] = v;
+      continue;
+    }
+    if (op.bias) v += op.bias[j];
+    if (op.relu) v = fmaxf(v, 0.f);
+    if (op.mask) v = op.mask[i * op.m_si + j * op.m_sj] > 0.f ? v : 0.f;
+    op.C[i * op.c_si + j * op.c_sj] = v;
+  }
+}
+
+GemmOp gemm_op(int I, int J, int R) {
+  GemmOp op;
+  memset(&op, 0, sizeof(op));
+  op.I = I;
+  op.J = J;
+  op.R = R;
+  op.r_split = R;
+  op.j_split = J;
+  op.ones_col = -1;
+  return op;
+}
+
+int launch_gemm(const GemmOp& op, const char* name, cudaStream_t st) {
+  if (op.I <= 0 || op.J <= 0) return SKGS_OK;
+  const dim3 grid((op.I + GM_TI - 1) / GM_TI, (op.J + GM_TJ - 1) / GM_TJ);
+  {
+    ProfScope prof_(name, st);
+    small_gemm_kernel<<<grid, GM_THREADS, 0, st>>>(op);
+  }
+  SKGS_CHECK_LAUNCH(name);
+  return SKGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// frequency encoders (freqencoder.cu:7-31): x0[m] = [enc_p(joints[m]) | enc_t(t)],
+// enc(x) = (x, sin(2^0 x), sin(2^0 x + pi/2), sin(2^1 x), ...) in blocks of D.  The argument arithmetic is the
+// reference's (scalbnf, one fp32 addition of fl32(pi/2)); the sine itself is the accurate sinf, not __sinf.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float freq_value(const float* x, int D, int c) {
+  if (c < D) return x[c];
+  const int col = c / D - 1, d = c % D, freq = col >> 1;
+  const float phase = (col & 1) ? 1.5707963267948966f : 0.f;
+  return sinf(__fadd_rn(scalbnf(x[d], freq), phase));
+}
+
+__global__ void joint_encode_kernel(int M, int deg_p, int deg_t, const float* __restrict__ joints,
+                                    const float* __restrict__ t, float* __restrict__ x0) {
+  const int Cp = 3 * (1 + 2 * deg_p), Ct = 1 + 2 * deg_t, enc = Cp + Ct;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * enc) return;
+  const int m = e / enc, c = e - m * enc;
+  x0[e] = c < Cp ? freq_value(joints + 3 * m, 3, c) : freq_value(t, 1, c - Cp);
+}
+
+// freqencoder.cu:36-62: dx[d] = g[d] + sum_f 2^f (g_sin * out_cos - g_cos * out_sin), g = sum of the gradients that
+// reached the encoded input (layer 0 and every skip layer)
+__global__ void joint_encode_bwd_kernel(int M, int deg_p, int enc, const float* __restrict__ x0, int n_users,
+                                        const float* __restrict__ dx0,
+                                        long long user_stride, float* __restrict__ dL_djoints) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * 3) return;
+  const int m = e / 3, d = e - m * 3;
+  const float* o = x0 + (size_t)m * enc;
+  auto g = [&](int c) {
+    float s = 0.f;
+    for (int u = 0; u < n_users; ++u) s += dx0[u * user_stride + (size_t)m * enc + c];
+    return s;
+  };
+  float r = g(d);
+  for (int f = 0; f < deg_p; ++f) {
+    const int cs = 3 + 6 * f + d, cc = cs + 3;
+    r += scalbnf(1.0f, f) * (g(cs) * o[cc] - g(cc) * o[cs]);
+  }
+  dL_djoints[e] = r;
+}
+
+// heads: out[m] = (q[4], d_rot[4], d_scale[3]); sk_r = normalize(q + (0,0,0,1)) with F.normalize's eps 1e-12
+__global__ void joint_head_kernel(int M, int n_out, int rotation_head, const float* __restrict__ out,
+                                  float* __restrict__ sk_r, float* __restrict__ d_rot, float* __restrict__ d_scale) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* o = out + (size_t)m * n_out;
+  float q[4] = {o[0], o[1], o[2], o[3]};
+  if (rotation_head) {
+    q[3] += 1.0f;
+    const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    for (int k = 0; k < 4; ++k) q[k] /= n;
+  }
+  for (int k = 0; k < 4; ++k) sk_r[4 * m + k] = q[k];
+  for (int k = 0; k < 4; ++k) d_rot[4 * m + k] = o[4 + k];
+  for (int k = 0; k < 3; ++k) d_scale[3 * m + k] = o[8 + k];
+}
+
+__global__ void joint_head_bwd_kernel(int M, int n_out, int rotation_head, const float* __restrict__ out,
+                                      const float* __restrict__ g_sk_r, const float* __restrict__ g_d_rot,
+                                      const float* __restrict__ g_d_scale, float* __restrict__ d_out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* o = out + (size_t)m * n_out;
+  float* d = d_out + (size_t)m * n_out;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g_sk_r)
+    for (int k = 0; k < 4; ++k) g[k] = g_sk_r[4 * m + k];
+  if (rotation_head) {
+    const float q[4] = {o[0], o[1], o[2], o[3] + 1.0f};
+    const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (nrm > 1e-12f) {  // d normalize: (g - q^ (q^ . g)) / |q|
+      const float inv = 1.0f / nrm;
+      float dot = 0.f;
+      for (int k = 0; k < 4; ++k) dot += q[k] * inv * g[k];
+      for (int k = 0; k < 4; ++k) g[k] = (g[k] - q[k] * inv * dot) * inv;
+    } else {
+      for (int k = 0; k < 4; ++k) g[k] *= 1e12f;
+    }
+  }
+  for (int k = 0; k < 4; ++k) d[k] = g[k];
+  for (int k = 0; k < 4; ++k) d[4 + k] = g_d_rot ? g_d_rot[4 * m + k] : 0.f;
+  for (int k = 0; k < 3; ++k) d[8 + k] = g_d_scale ? g_d_scale[3 * m + k] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side description of the network
+// ---------------------------------------------------------------------------------------------------------------
+struct Net {
+  int M, enc, width, depth, n_out;
+  int in_dim[33];          // input width of hidden layer i (i < depth) and of the heads (i == depth)
+  bool skip_in[33];        // that input is [previous activation | x0]
+  long long w_off[33], b_off[33], total;
+  int x0_users, user_of_layer[33];  // which dx0 buffer receives the gradient of layer i's x0 part
+  // workspace offsets (floats)
+  long long o_x0, o_act, o_out, o_dza, o_dzb, o_dzh, o_dx0, ws_floats;
+};
+
+int describe(const skgs_joint_mlp* n, Net& N) {
+  SKGS_CHECK_ARG(n != nullptr, "joint_mlp: null descriptor");
+  SKGS_CHECK_ARG(n->M >= 0 && n->degree_p >= 0 && n->degree_t >= 0 && n->degree_p <= 16 && n->degree_t <= 16,
+                 "joint_mlp: invalid M %d / encoder degrees %d, %d", n->M, n->degree_p, n->degree_t);
+  SKGS_CHECK_ARG(n->width > 0 && n->depth >= 1 && n->depth <= 32, "joint_mlp: invalid width %d / depth %d", n->width,
+                 n->depth);
+  SKGS_CHECK_ARG(n->n_out == 11, "joint_mlp: the heads are (4, 4, 3) = 11 outputs (sk_gs.py:519), got %d", n->n_out);
+  N.M = n->M;
+  N.enc = 3 * (1 + 2 * n->degree_p) + (1 + 2 * n->degree_t);
+  N.width = n->width;
+  N.depth = n->depth;
+  N.n_out = n->n_out;
+  long long off = 0;
+  N.x0_users = 0;
+  for (int i = 0; i <= N.depth; ++i) {
+    N.skip_in[i] = i > 0 && ((n->skip_mask >> (i - 1)) & 1);
+    N.in_dim[i] = i == 0 ? N.enc : N.width + (N.skip_in[i] ? N.enc : 0);
+    N.user_of_layer[i] = (i == 0 || N.skip_in[i]) ? N.x0_users++ : -1;
+    const int out = i < N.depth ? N.width : N.n_out;
+    N.w_off[i] = off;
+    off += (long long)out * N.in_dim[i];
+    N.b_off[i] = off;
+    off += out;
+  }
+  SKGS_CHECK_ARG(N.x0_users <= MAX_X0_USERS, "joint_mlp: at most %d skip connections", MAX_X0_USERS - 1);
+  N.total = off;
+  long long w = 0;
+  auto take = [&](long long count) {
+    const long long at = w;
+    w += (count + 63) / 64 * 64;
+    return at;
+  };
+  N.o_x0 = take((long long)N.M * N.enc);
+  N.o_act = take((long long)N.depth * N.M * N.width);
+  N.o_out = take((long long)N.M * N.n_out);
+  N.o_dza = take((long long)N.M * N.width);
+  N.o_dzb = take((long long)N.M * N.width);
+  N.o_dzh = take((long long)N.M * N.n_out);
+  N.o_dx0 = take((long long)N.x0_users * N.M * N.enc);
+  N.ws_floats = w;
+  return SKGS_OK;
+}
+
+}  // namespace
+}  // namespace skgs
+
+using namespace skgs;
+
+extern "C" {
+
+int skgs_joint_mlp_layout(const skgs_joint_mlp* net, int64_t* weight_offsets, int64_t* bias_offsets,
+                          int32_t* in_dims, int64_t* total) {
+  Net N;
+  if (int rc = describe(net, N)) return rc;
+  for (int i = 0; i <= N.depth; ++i) {
+    if (weight_offsets) weight_offsets[i] = N.w_off[i];
+    if (bias_offsets) bias_offsets[i] = N.b_off[i];
+    if (in_dims) in_dims[i] = N.in_dim[i];
+  }
+  if (total) *total = N.total;
+  return SKGS_OK;
+}
+
+size_t skgs_joint_mlp_workspace_bytes(const skgs_joint_mlp* net) {
+  Net N;
+  if (describe(net, N)) return 0;
+  return (size_t)N.ws_floats * sizeof(float) + 256;
+}
+
+int skgs_joint_mlp_forward(const skgs_joint_mlp* net, const float* joints, const float* t, float* sk_r, float* d_rot,
+                           float* d_scale, void* workspace, void* stream) {
+  Net N;
+  if (int rc = describe(net, N)) return rc;
+  if (N.M == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(net->theta && joints && t && sk_r && d_rot && d_scale && workspace, "joint_mlp_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  float* x0 = ws + N.o_x0;
+  const float* theta = net->theta;
+  {
+    ProfScope prof_("joint_encode_kernel", st);
+    joint_encode_kernel<<<(N.M * N.enc + 127) / 128, 128, 0, st>>>(N.M, net->degree_p, net->degree_t, joints, t, x0);
+  }
+  SKGS_CHECK_LAUNCH("joint_encode_kernel");
+  for (int i = 0; i <= N.depth; ++i) {
+    const bool head = i == N.depth;
+    const int out = head ? N.n_out : N.width, in = N.in_dim[i];
+    GemmOp op = gemm_op(N.M, out, in);
+    if (i == 0) {
+      op.A = x0;
+      op.a_si = N.enc;
+      op.a_sr = 1;
+    } else {
+      op.A = ws + N.o_act + (long long)(i - 1) * N.M * N.width;
+      op.a_si = N.width;
+      op.a_sr = 1;
+      if (N.skip_in[i]) {
+        op.r_split = N.width;
+        op.A2 = x0;
+        op.a2_si = N.enc;
+        op.a2_sr = 1;
+      }
+    }
+    op.B = theta + N.w_off[i];
+    op.b_sj = in;
+    op.b_sr = 1;
+    op.bias = theta + N.b_off[i];
+    op.relu = head ? 0 : 1;
+    op.C = head ? ws + N.o_out : ws + N.o_act + (long long)i * N.M * N.width;
+    op.c_si = out;
+    op.c_sj = 1;
+    if (int rc = launch_gemm(op, head ? "joint_mlp_head_gemm" : "joint_mlp_layer_gemm", st)) return rc;
+  }
+  {
+    ProfScope prof_("joint_head_kernel", st);
+    joint_head_kernel<<<(N.M + 63) / 64, 64, 0, st>>>(N.M, N.n_out, net->rotation_head, ws + N.o_out, sk_r, d_rot,
+                                                      d_scale);
+  }
+  SKGS_CHECK_LAUNCH("joint_head_kernel");
+  return SKGS_OK;
+}
+
+int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, const float* dL_dd_rot,
+                            const float* dL_dd_scale, float* dL_dtheta, float* dL_djoints, void* workspace,
+                            void* stream) {
+  Net N;
+  if (int rc = describe(net, N)) return rc;
+  if (N.M == 0) return SKGS_OK;
+  SKGS_CHECK_ARG(net->theta && dL_dtheta && workspace, "joint_mlp_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  const float* x0 = ws + N.o_x0;
+  const float* theta = net->theta;
+  float* dzh = ws + N.o_dzh;
+  {
+    ProfScope prof_("joint_head_bwd_kernel", st);
+    joint_head_bwd_kernel<<<(N.M + 63) / 64, 64, 0, st>>>(N.M, N.n_out, net->rotation_head, ws + N.o_out, dL_dsk_r,
+                                                          dL_dd_rot, dL_dd_scale, dzh);
+  }
+  SKGS_CHECK_LAUNCH("joint_head_bwd_kernel");
+  // dZ of layer i (pre-activation gradient, [M, out_i]); the heads first, then hidden layers depth-1 .. 0
+  const float* dz = dzh;
+  for (int i = N.depth; i >= 0; --i) {
+    const bool head = i == N.depth;
+    const int out = head ? N.n_out : N.width, in = N.in_dim[i];
+    const float* prev = i == 0 ? x0 : ws + N.o_act + (long long)(i - 1) * N.M * N.width;
+    const int prev_w = i == 0 ? N.enc : N.width;
+    // dW[n][k] = sum_m dZ[m][n] * input[m][k], plus the bias gradient as the "ones" column k == in
+    {
+      GemmOp op = gemm_op(out, in + 1, N.M);
+      op.A = dz;
+      op.a_si = 1;
+      op.a_sr = out;
+      op.B = prev;
+      op.b_sj = 1;
+      op.b_sr = prev_w;
+      if (i > 0 && N.skip_in[i]) {
+        op.j_split = N.width;
+        op.B2 = x0;
+        op.b2_sj = 1;
+        op.b2_sr = N.enc;
+      }
+      op.ones_col = in;
+      op.C = dL_dtheta + N.w_off[i];
+      op.c_si = in;
+      op.c_sj = 1;
+      op.C_ones = dL_dtheta + N.b_off[i];
+      if (int rc = launch_gemm(op, "joint_mlp_dw_gemm", st)) return rc;
+    }
+    // gradient w.r.t. the encoded input, where this layer reads it
+    if (N.user_of_layer[i] >= 0 && dL_djoints) {
+      GemmOp op = gemm_op(N.M, N.enc, out);
+      op.A = dz;
+      op.a_si = out;
+      op.a_sr = 1;
+      op.B = theta + N.w_off[i] + (i == 0 ? 0 : N.width);
+      op.b_sj = 1;
+      op.b_sr = in;
+      op.C = ws + N.o_dx0 + (long long)N.user_of_layer[i] * N.M * N.enc;
+      op.c_si = N.enc;
+      op.c_sj = 1;
+      if (int rc = launch_gemm(op, "joint_mlp_dx0_gemm", st)) return rc;
+    }
+    // dZ of the previous hidden layer: (dZ W)[:, :width] masked by that layer's ReLU
+    if (i > 0) {
+      float* dz_prev = ws + (((N.depth - i) & 1) ? N.o_dzb : N.o_dza);
+      GemmOp op = gemm_op(N.M, N.width, out);
+      op.A = dz;
+      op.a_si = out;
+      op.a_sr = 1;
+      op.B = theta + N.w_off[i];
+      op.b_sj = 1;
+      op.b_sr = in;
+      op.mask = prev;
+      op.m_si = N.width;
+      op.m_sj = 1;
+      op.C = dz_prev;
+      op.c_si = N.width;
+      op.c_sj = 1;
+      if (int rc = launch_gemm(op, "joint_mlp_da_gemm", st)) return rc;
+      dz = dz_prev;
+    }
+  }
+  if (dL_djoints) {
+    ProfScope prof_("joint_encode_bwd_kernel", st);
+    joint_encode_bwd_kernel<<<(N.M * 3 + 63) / 64, 64, 0, st>>>(N.M, net->degree_p, N.enc, x0, N.x0_users,
+                                                                ws + N.o_dx0, (long long)N.M * N.enc, dL_djoints);
+    SKGS_CHECK_LAUNCH("joint_encode_bwd_kernel");
+  }
+  return SKGS_OK;
+}
+
+}  // extern "C"

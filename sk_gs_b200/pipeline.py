@@ -34,9 +34,11 @@ class HotPath:
     """Holds the parameters of one synthetic scene on a device and runs the per-view step."""
 
     def __init__(self, scene: Scene, device='cuda', mode: str = 'W', requires_grad: bool = True,
-                 merged_sh: bool = False):
+                 merged_sh: bool = False, joint_mlp: bool = False, mlp_seed: int = 0, head_std: float = 1e-6):
         """`merged_sh`: keep the SH coefficients as ONE [P,16,3] parameter ('shs'; 'f_dc' / 'f_rest' become views of it)
-        instead of the reference's two Parameters that are concatenated on every step (gaussian_splatting.py:155-157)."""
+        instead of the reference's two Parameters that are concatenated on every step (gaussian_splatting.py:155-157).
+        `joint_mlp`: the joint rotations come from the joint-rotation network (sk_gs.py:1074-1076) evaluated
+        at time `self.t` instead of being leaf parameters; its flat parameter vector is `params['theta']`."""
         self.scene = scene
         self.device = torch.device(device)
         self.mode = mode
@@ -50,13 +52,32 @@ class HotPath:
             self.params['f_dc'], self.params['f_rest'] = shs.detach()[:, :1], shs.detach()[:, 1:]
         self.sp_radius = scene.sp_radius.to(self.device).clone().requires_grad_(requires_grad and mode != 'W')
         self.sp_weight = scene.sp_weight.to(self.device).clone().requires_grad_(requires_grad and mode != 'W')
+        self.mlp = None
+        if joint_mlp:
+            from .deform_net import SimpleDeformationNetwork
+            gen_state = torch.random.get_rng_state()
+            torch.manual_seed(mlp_seed)
+            self.mlp = SimpleDeformationNetwork(pos_enc_p_cfg=dict(degree=10), pos_enc_t_cfg=dict(degree=6), width=256,
+                                                depth=8, skips=(4,), rotation_head=True)  # exps/default.yaml:48-55
+            self.mlp.reset_heads(head_std)
+            torch.random.set_rng_state(gen_state)
+            self.mlp.to(self.device)
+            self.mlp.theta.requires_grad_(requires_grad)
+            self.params['theta'] = self.mlp.theta
+            for n in ('sk_r', 'sk_d_rot', 'sk_d_scale'):  # produced by the network now
+                del self.params[n]
+            self.t = torch.tensor([0.37], device=self.device)
         self.parents = scene.parents.to(self.device)
         self.root = scene.root
         self.settings = [raster_settings_for(c, self.device, scene.sh_degree) for c in scene.cameras]
 
     def deform(self):
         p = self.params
-        out = fk_lbs(p['xyz'], p['joints'], p['sk_r'], p['sk_d_rot'], p['sk_d_scale'], p['g_tr'], self.parents,
+        if self.mlp is not None:
+            sk_r, sk_d_rot, sk_d_scale = self.mlp(p['joints'], self.t)
+        else:
+            sk_r, sk_d_rot, sk_d_scale = p['sk_r'], p['sk_d_rot'], p['sk_d_scale']
+        out = fk_lbs(p['xyz'], p['joints'], sk_r, sk_d_rot, sk_d_scale, p['g_tr'], self.parents,
                      self.root, K=self.K, mode=self.mode, sp_W=p['sp_W'] if self.mode == 'W' else None,
                      sp_radius=self.sp_radius if self.mode != 'W' else None,
                      sp_weight=self.sp_weight if self.mode == 'weighted_kernel' else None)
@@ -97,8 +118,17 @@ class HotPath:
         with torch.no_grad():
             p = self.params
             W = self.mode == 'W'
+            cm = None
+            if self.mlp is not None:
+                from .deform_net import joint_mlp_backward_raw, joint_mlp_forward_raw
+                if not hasattr(self, '_mlp_buffers'):
+                    self._mlp_buffers = {}
+                (sk_r, sk_d_rot, sk_d_scale), cm = joint_mlp_forward_raw(self.mlp.cfg, p['theta'].data, p['joints'],
+                                                                         self.t, out=self._mlp_buffers.setdefault(view, {}))
+            else:
+                sk_r, sk_d_rot, sk_d_scale = p['sk_r'], p['sk_d_rot'], p['sk_d_scale']
             (d_xyz, d_rot, d_scale, sk_T, weights, indices), c1 = fk_lbs_forward_raw(
-                p['xyz'], p['joints'], p['sk_r'], p['sk_d_rot'], p['sk_d_scale'], p['g_tr'], self.parents, self.root,
+                p['xyz'], p['joints'], sk_r, sk_d_rot, sk_d_scale, p['g_tr'], self.parents, self.root,
                 K=self.K, mode=self.mode, sp_W=p['sp_W'] if W else None, sp_radius=None if W else self.sp_radius,
                 sp_weight=self.sp_weight if self.mode == 'weighted_kernel' else None)
             (points, scales, rotations, opacity), c2 = assemble_forward_raw(p['xyz'], p['scaling'], p['rotation'],
@@ -118,7 +148,7 @@ class HotPath:
                                                        **(loss or {}))
             # with an arena (sk_gs_b200.dist.GradArena) every final gradient is written straight into its slot of the
             # flat all-reduce buffer: no packing copies before the exchange
-            A = (lambda n: arena.view(n)) if arena is not None else (lambda n: None)
+            A = (lambda n: arena.view(n) if n in arena.offsets else None) if arena is not None else (lambda n: None)
             g = DGR.rasterize_backward(st, dL_dimage, out={'means3D': A('xyz'), 'means2D': A('viewspace_points'),
                                                           'shs': A('shs')})
             _, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
@@ -130,17 +160,22 @@ class HotPath:
             d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight = fk_lbs_backward_raw(
                 c1, dd_xyz, dd_rot, dd_scale, compact_sp_W=compact_sp_W,
                 out={n: A(n) for n in ('joints', 'sk_r', 'sk_d_rot', 'sk_d_scale', 'g_tr', 'sp_W')})
+            d_theta = None
+            if cm is not None:  # back through the joint-rotation network; joints also feed the network input
+                d_theta, d_joints_net = joint_mlp_backward_raw(cm, d_sk_r, d_sk_d_rot, d_sk_d_scale,
+                                                               out={'theta': A('theta')})
+                d_joints.add_(d_joints_net)
         grads = {'xyz': dxyz, 'scaling': dscaling, 'rotation': drotation, 'opacity': dopacity, 'shs': g['shs'],
                  'f_dc': g['shs'][:, :1], 'f_rest': g['shs'][:, 1:], 'sp_W': d_sp_W, 'joints': d_joints, 'sk_r': d_sk_r,
                  'sk_d_rot': d_sk_d_rot, 'sk_d_scale': d_sk_d_scale, 'g_tr': d_g_tr, 'viewspace_points': g['means2D'],
-                 'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight}
+                 'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight, 'theta': d_theta}
         if join_after is not None:
             join_after()
         if join_mid is not None:
             join_mid()
         out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
                'loss_terms': loss_terms,
-               'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, p['sk_d_rot'], p['sk_d_scale'], p['g_tr'],
+               'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, sk_d_rot, sk_d_scale, p['g_tr'],
                                                  weights, indices)}
         return out, grads
 

@@ -21,7 +21,7 @@ from .pipeline import HotPath
 DEFAULT_LRS = {
     'xyz': 1e-3 * 0.16, 'shs': (1e-3 * 2.5, 1e-3 * 2.5 / 20, 48, 3), 'opacity': 1e-3 * 50., 'scaling': 1e-3 * 5.0,
     'rotation': 1e-3 * 1.0, 'sp_W': 1e-3, 'joints': 1e-3 * 0.1, 'sk_r': 1e-3, 'sk_d_rot': 1e-3, 'sk_d_scale': 1e-3,
-    'g_tr': 1e-3,
+    'g_tr': 1e-3, 'theta': 1e-3,  # lr * lr_deform_scale (exps/default.yaml:64)
 }
 
 

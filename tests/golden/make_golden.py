@@ -12,6 +12,7 @@ be imported UNMODIFIED from /root/reference.  Functions exercised (all torch, CP
   my_ext/ops_3d/coord_trans_opencv.py    : perspective                          -> cam.npz
   networks/losses/ssim.py, image_loss.py : SSIM_Loss, ImageLoss (+ autograd)    -> loss.npz
   torch.optim.Adam (the reference's optimizer, gaussian_splatting.py:445-453)   -> adam.npz
+  networks/sk_gs.py                      : SimpleDeformationNetwork ('freq_torch' encoders, fp64) -> deform_net.npz
 """
 import importlib
 import importlib.abc
@@ -134,6 +135,7 @@ def main():
     np.savez(os.path.join(OUT, 'cam.npz'), Tv2c_800=Tv2c.numpy(), Tv2c_1080p=Tv2c2.numpy())
     make_loss()
     make_adam()
+    make_deform_net()
     print('golden vectors written to', OUT)
 
 
@@ -167,6 +169,42 @@ def make_loss():
                         f'g_ssim_{tag}_{i}': g_ss.numpy(), f'g_total_{tag}_{i}': g_total.numpy()})
         out.update({f'img_{i}': img.numpy(), f'gt_{i}': gt.numpy()})
     np.savez_compressed(os.path.join(OUT, 'loss.npz'), n=np.int64(len(cases)), **out)
+
+
+def make_deform_net():
+    """The reference's joint-rotation network (networks/sk_gs.py:134-164) with the configuration of
+    exps/default.yaml:48-55 but the pure-torch encoder variant (the CUDA one cannot run here), in float64, small width so
+    the fixture stays small; outputs and gradients w.r.t. joints and every parameter."""
+    sk = importlib.import_module('networks.sk_gs')
+    torch.manual_seed(20241017 + 300)
+    out = {}
+    cases = [dict(M=16, width=32, depth=8, skips=(4,)), dict(M=5, width=16, depth=4, skips=(1, 2))]
+    for ci, c in enumerate(cases):
+        net = sk.SimpleDeformationNetwork(p_in_channels=3, t_in_channels=1, out_channels=[4, 4, 3], width=c['width'],
+                                          depth=c['depth'], skips=c['skips'], pos_enc_p='freq_torch',
+                                          pos_enc_p_cfg=dict(degree=10), pos_enc_t='freq_torch',
+                                          pos_enc_t_cfg=dict(degree=6)).double()
+        for m in net.dynamic_net.last:  # the reference's 1e-6 init would put every gradient at noise level
+            torch.nn.init.normal_(m.weight, std=0.05)
+            torch.nn.init.normal_(m.bias, std=0.05)
+        joints = (torch.randn(c['M'], 3, dtype=torch.float64) * 0.4).requires_grad_(True)
+        t = torch.tensor([0.37], dtype=torch.float64)
+        o_r, o_rot, o_s = net(joints, t)
+        g_r, g_rot, g_s = torch.randn_like(o_r), torch.randn_like(o_rot), torch.randn_like(o_s)
+        params = list(net.dynamic_net.net.parameters()) + list(net.dynamic_net.last.parameters())
+        grads = torch.autograd.grad([o_r, o_rot, o_s], [joints] + params, [g_r, g_rot, g_s])
+        out.update({f'joints{ci}': joints.detach().numpy(), f't{ci}': t.numpy(), f'o_r{ci}': o_r.detach().numpy(),
+                    f'o_rot{ci}': o_rot.detach().numpy(), f'o_s{ci}': o_s.detach().numpy(), f'g_r{ci}': g_r.numpy(),
+                    f'g_rot{ci}': g_rot.numpy(), f'g_s{ci}': g_s.numpy(), f'd_joints{ci}': grads[0].numpy(),
+                    f'cfg{ci}': np.array([c['M'], c['width'], c['depth']] + list(c['skips']))})
+        layers = list(net.dynamic_net.net) + list(net.dynamic_net.last)
+        for li, layer in enumerate(layers):
+            out[f'w{ci}_{li}'] = layer.weight.detach().numpy()
+            out[f'b{ci}_{li}'] = layer.bias.detach().numpy()
+        for li in range(len(layers)):
+            out[f'dw{ci}_{li}'] = grads[1 + 2 * li].numpy()
+            out[f'db{ci}_{li}'] = grads[2 + 2 * li].numpy()
+    np.savez_compressed(os.path.join(OUT, 'deform_net.npz'), n=np.int64(len(cases)), **out)
 
 
 def make_adam():
