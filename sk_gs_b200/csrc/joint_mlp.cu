@@ -9,8 +9,8 @@
 //
 // Round-1 form: M is tiny, so every matrix product is one launch of a small strided fp32 GEMM (`small_gemm_kernel`,
 // exact FFMA chains, no tensor cores: results must match the reference's fp32 Linear layers) with bias, ReLU, ReLU-mask,
-// skip-concatenation and bias-gradient fused in; 11 launches forward, 21 backward, all capturable in the step's CUDA
-// graph.  (Next: one thread-block cluster with the activations in distributed shared memory.)
+// skip-concatenation and bias-gradient fused in, and the independent products of one backward layer (dW, dZ_prev, dx0)
+// share a launch: 11 launches forward, 11 backward, all capturable in the step's CUDA graph.  (Next: one thread-block cluster with the activations in distributed shared memory.)
 #include <cstring>
 
 #include "common.cuh"
@@ -22,7 +22,7 @@ constexpr int GM_TI = 32;                    // rows of C per CTA: one per lane
 constexpr int GM_WARPS = 4;
 constexpr int GM_JW = 2;                     // columns of C per warp
 constexpr int GM_TJ = GM_WARPS * GM_JW;      // columns of C per CTA
-constexpr int GM_RC = 64;                    // reduction chunk staged in shared memory
+constexpr int GM_RC = 128;                   // reduction chunk staged in shared memory
 constexpr int GM_LD = GM_RC + 4;             // row stride: 16-byte aligned rows, conflict-free 128-bit loads
 constexpr int GM_THREADS = GM_WARPS * 32;
 constexpr int MAX_X0_USERS = 8;
@@ -30,49 +30,99 @@ constexpr int MAX_X0_USERS = 8;
 // C(i,j) = epilogue( sum_r A(i,r) * B(j,r) ),  i < I, j < J, r < R; every operand is addressed through element strides.
 struct GemmOp {
   int I, J, R;
-  const float* A;  long long a_si, a_sr;
-  const float* A2; long long a2_si, a2_sr; int r_split;  // r >= r_split reads A2(i, r - r_split)  (skip concatenation)
-  const float* B;  long long b_sj, b_sr;
-  const float* B2; long long b2_sj, b2_sr; int j_split;  // j >= j_split reads B2(j - j_split, r)
+  const float* A;  int a_si, a_sr;                       // (every operand here is far below 2^31 elements)
+  const float* A2; int a2_si, a2_sr; int r_split;         // r >= r_split reads A2(i, r - r_split)  (skip concatenation)
+  const float* B;  int b_sj, b_sr;
+  const float* B2; int b2_sj, b2_sr; int j_split;         // j >= j_split reads B2(j - j_split, r)
   int ones_col;                                           // B(ones_col, r) = 1: column sums of A (bias gradient)
-  float* C; long long c_si, c_sj;
+  float* C; int c_si, c_sj;
   float* C_ones;                                          // where column `ones_col` of C goes (contiguous in i)
   const float* bias;                                      // + bias[j]
   int relu;                                               // max(., 0)
-  const float* mask; long long m_si, m_sj;                // * (mask(i,j) > 0): ReLU backward
+  const float* mask; int m_si, m_sj;                      // * (mask(i,j) > 0): ReLU backward
 };
 
-__device__ __forceinline__ float gemm_a(const GemmOp& op, int i, int r) {
-  if (i >= op.I || r >= op.R) return 0.f;
-  return r < op.r_split ? op.A[i * op.a_si + r * op.a_sr] : op.A2[i * op.a2_si + (r - op.r_split) * op.a2_sr];
+// Operand access is split in two so that the loads of a chunk can all be in flight at once: `*_addr` yields an address
+// that is always safe to read (out-of-range elements read the operand's first element), `*_value` applies the padding
+// rule to the loaded value when it is written to shared memory.  (A load whose result is selected right away, or that
+// sits behind a data-dependent branch, makes the in-order warp wait for it: 40 serialised L2 round trips per chunk.)
+// All of this works on a register-resident copy of the descriptor: the launch batches several products, so the
+// descriptor is indexed dynamically in parameter space and every field access would otherwise be an LDC round trip.
+__device__ __forceinline__ const float* gemm_a_addr(const GemmOp& op, int i, int r) {
+  const int off = r < op.r_split ? i * op.a_si + r * op.a_sr : i * op.a2_si + (r - op.r_split) * op.a2_sr;
+  const float* base = r < op.r_split ? op.A : op.A2;
+  return (i < op.I && r < op.R) ? base + off : op.A;
+}
+__device__ __forceinline__ float gemm_a_value(const GemmOp& op, int i, int r, float loaded) {
+  return (i < op.I && r < op.R) ? loaded : 0.f;
+}
+__device__ __forceinline__ const float* gemm_b_addr(const GemmOp& op, int j, int r) {
+  const int off = j < op.j_split ? j * op.b_sj + r * op.b_sr : (j - op.j_split) * op.b2_sj + r * op.b2_sr;
+  const float* base = j < op.j_split ? op.B : op.B2;
+  return (j < op.J && r < op.R && j != op.ones_col) ? base + off : op.B;
+}
+__device__ __forceinline__ float gemm_b_value(const GemmOp& op, int j, int r, float loaded) {
+  return (j < op.J && r < op.R) ? (j == op.ones_col ? 1.f : loaded) : 0.f;
 }
 
-__device__ __forceinline__ float gemm_b(const GemmOp& op, int j, int r) {
-  if (j >= op.J || r >= op.R) return 0.f;
-  if (j == op.ones_col) return 1.f;
-  return j < op.j_split ? op.B[j * op.b_sj + r * op.b_sr] : op.B2[(j - op.j_split) * op.b2_sj + r * op.b2_sr];
-}
+// Up to GM_BATCH independent products per launch (e.g. dW, dZ_prev and dx0 of one layer): dependent launches cost more
+// than these kernels run, so everything that may run side by side shares a grid.
+constexpr int GM_BATCH = 3;
+struct GemmBatch {
+  GemmOp op[GM_BATCH];
+  int block_start[GM_BATCH + 1];
+  int count;
+};
 
-__global__ void __launch_bounds__(GM_THREADS) small_gemm_kernel(const __grid_constant__ GemmOp op) {
+__global__ void __launch_bounds__(GM_THREADS) small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
   __shared__ __align__(16) float As[GM_TI][GM_LD];
   __shared__ __align__(16) float Bs[GM_TJ][GM_LD];
+  constexpr int A_PER = GM_TI * GM_RC / GM_THREADS, B_PER = GM_TJ * GM_RC / GM_THREADS;
+  int which = 0;
+  while (which + 1 < batch.count && (int)blockIdx.x >= batch.block_start[which + 1]) ++which;
+  const GemmOp op = batch.op[which];  // one copy into registers (see above)
+  const int local = (int)blockIdx.x - batch.block_start[which];
+  const int blocks_i = (op.I + GM_TI - 1) / GM_TI;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i0 = blockIdx.x * GM_TI, j0 = blockIdx.y * GM_TJ;
+  const int i0 = (local % blocks_i) * GM_TI, j0 = (local / blocks_i) * GM_TJ;
   const bool a_fast_r = op.a_sr == 1, b_fast_r = op.b_sr == 1;  // walk the contiguous direction with consecutive threads
   float acc[GM_JW];
 #pragma unroll
   for (int jj = 0; jj < GM_JW; ++jj) acc[jj] = 0.f;
 
-  for (int r0 = 0; r0 < op.R; r0 += GM_RC) {
-    for (int e = tid; e < GM_TI * GM_RC; e += GM_THREADS) {
+  // The operands are tiny and live in L2: the kernel is pure load latency, so every thread issues ALL its loads of a
+  // chunk back to back into registers, and the next chunk's loads are in flight while the current one is multiplied.
+  float ra[A_PER], rb[B_PER];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int u = 0; u < A_PER; ++u) {
+      const int e = tid + u * GM_THREADS;
       const int ii = a_fast_r ? e / GM_RC : e % GM_TI, rr = a_fast_r ? e % GM_RC : e / GM_TI;
-      As[ii][rr] = gemm_a(op, i0 + ii, r0 + rr);
+      ra[u] = __ldg(gemm_a_addr(op, i0 + ii, r0 + rr));
     }
-    for (int e = tid; e < GM_TJ * GM_RC; e += GM_THREADS) {
+#pragma unroll
+    for (int u = 0; u < B_PER; ++u) {
+      const int e = tid + u * GM_THREADS;
       const int jj = b_fast_r ? e / GM_RC : e % GM_TJ, rr = b_fast_r ? e % GM_RC : e / GM_TJ;
-      Bs[jj][rr] = gemm_b(op, j0 + jj, r0 + rr);
+      rb[u] = __ldg(gemm_b_addr(op, j0 + jj, r0 + rr));
+    }
+  };
+  fetch(0);
+  for (int r0 = 0; r0 < op.R; r0 += GM_RC) {
+#pragma unroll
+    for (int u = 0; u < A_PER; ++u) {
+      const int e = tid + u * GM_THREADS;
+      const int ii = a_fast_r ? e / GM_RC : e % GM_TI, rr = a_fast_r ? e % GM_RC : e / GM_TI;
+      As[ii][rr] = gemm_a_value(op, i0 + ii, r0 + rr, ra[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < B_PER; ++u) {
+      const int e = tid + u * GM_THREADS;
+      const int jj = b_fast_r ? e / GM_RC : e % GM_TJ, rr = b_fast_r ? e % GM_RC : e / GM_TJ;
+      Bs[jj][rr] = gemm_b_value(op, j0 + jj, r0 + rr, rb[u]);
     }
     __syncthreads();
+    if (r0 + GM_RC < op.R) fetch(r0 + GM_RC);
 #pragma unroll 4
     for (int rr = 0; rr < GM_RC; rr += 4) {
       const float4 a = *reinterpret_cast<const float4*>(&As[lane][rr]);
@@ -118,16 +168,26 @@ GemmOp gemm_op(int I, int J, int R) {
   return op;
 }
 
-int launch_gemm(const GemmOp& op, const char* name, cudaStream_t st) {
-  if (op.I <= 0 || op.J <= 0) return SKGS_OK;
-  const dim3 grid((op.I + GM_TI - 1) / GM_TI, (op.J + GM_TJ - 1) / GM_TJ);
+int launch_gemms(const GemmOp* ops, int n, const char* name, cudaStream_t st) {
+  GemmBatch b;
+  memset(&b, 0, sizeof(b));
+  for (int k = 0; k < n; ++k) {
+    if (ops[k].I <= 0 || ops[k].J <= 0) continue;
+    b.op[b.count] = ops[k];
+    b.block_start[b.count + 1] =
+        b.block_start[b.count] + ((ops[k].I + GM_TI - 1) / GM_TI) * ((ops[k].J + GM_TJ - 1) / GM_TJ);
+    ++b.count;
+  }
+  if (b.count == 0) return SKGS_OK;
   {
     ProfScope prof_(name, st);
-    small_gemm_kernel<<<grid, GM_THREADS, 0, st>>>(op);
+    small_gemm_kernel<<<b.block_start[b.count], GM_THREADS, 0, st>>>(b);
   }
   SKGS_CHECK_LAUNCH(name);
   return SKGS_OK;
 }
+
+int launch_gemm(const GemmOp& op, const char* name, cudaStream_t st) { return launch_gemms(&op, 1, name, st); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // frequency encoders (freqencoder.cu:7-31): x0[m] = [enc_p(joints[m]) | enc_t(t)],
@@ -153,23 +213,28 @@ __global__ void joint_encode_kernel(int M, int deg_p, int deg_t, const float* __
 // freqencoder.cu:36-62: dx[d] = g[d] + sum_f 2^f (g_sin * out_cos - g_cos * out_sin), g = sum of the gradients that
 // reached the encoded input (layer 0 and every skip layer)
 __global__ void joint_encode_bwd_kernel(int M, int deg_p, int enc, const float* __restrict__ x0, int n_users,
-                                        const float* __restrict__ dx0,
-                                        long long user_stride, float* __restrict__ dL_djoints) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= M * 3) return;
-  const int m = e / 3, d = e - m * 3;
+                                        const float* __restrict__ dx0, long long user_stride,
+                                        float* __restrict__ dL_djoints) {
+  // one warp per (joint, coordinate): lane 0 takes the pass-through term, lane f + 1 frequency f (deg_p <= 16)
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= M * 3) return;
+  const int m = w / 3, d = w - m * 3;
   const float* o = x0 + (size_t)m * enc;
-  auto g = [&](int c) {
-    float s = 0.f;
-    for (int u = 0; u < n_users; ++u) s += dx0[u * user_stride + (size_t)m * enc + c];
-    return s;
-  };
-  float r = g(d);
-  for (int f = 0; f < deg_p; ++f) {
-    const int cs = 3 + 6 * f + d, cc = cs + 3;
-    r += scalbnf(1.0f, f) * (g(cs) * o[cc] - g(cc) * o[cs]);
+  const float* g = dx0 + (size_t)m * enc;
+  float r = 0.f;
+  if (lane == 0) {
+    for (int u = 0; u < n_users; ++u) r += g[u * user_stride + d];
+  } else if (lane <= deg_p) {
+    const int f = lane - 1, cs = 3 + 6 * f + d, cc = cs + 3;
+    float gs = 0.f, gc = 0.f;
+    for (int u = 0; u < n_users; ++u) {
+      gs += g[u * user_stride + cs];
+      gc += g[u * user_stride + cc];
+    }
+    r = scalbnf(1.0f, f) * (gs * o[cc] - gc * o[cs]);
   }
-  dL_djoints[e] = r;
+  r = warp_sum(r);
+  if (lane == 0) dL_djoints[w] = r;
 }
 
 // heads: out[m] = (q[4], d_rot[4], d_scale[3]); sk_r = normalize(q + (0,0,0,1)) with F.normalize's eps 1e-12
@@ -376,6 +441,8 @@ int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, co
     const int out = head ? N.n_out : N.width, in = N.in_dim[i];
     const float* prev = i == 0 ? x0 : ws + N.o_act + (long long)(i - 1) * N.M * N.width;
     const int prev_w = i == 0 ? N.enc : N.width;
+    GemmOp ops[GM_BATCH];
+    int n_ops = 0;
     // dW[n][k] = sum_m dZ[m][n] * input[m][k], plus the bias gradient as the "ones" column k == in
     {
       GemmOp op = gemm_op(out, in + 1, N.M);
@@ -396,7 +463,7 @@ int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, co
       op.c_si = in;
       op.c_sj = 1;
       op.C_ones = dL_dtheta + N.b_off[i];
-      if (int rc = launch_gemm(op, "joint_mlp_dw_gemm", st)) return rc;
+      ops[n_ops++] = op;
     }
     // gradient w.r.t. the encoded input, where this layer reads it
     if (N.user_of_layer[i] >= 0 && dL_djoints) {
@@ -410,9 +477,10 @@ int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, co
       op.C = ws + N.o_dx0 + (long long)N.user_of_layer[i] * N.M * N.enc;
       op.c_si = N.enc;
       op.c_sj = 1;
-      if (int rc = launch_gemm(op, "joint_mlp_dx0_gemm", st)) return rc;
+      ops[n_ops++] = op;
     }
     // dZ of the previous hidden layer: (dZ W)[:, :width] masked by that layer's ReLU
+    const float* dz_next = dz;
     if (i > 0) {
       float* dz_prev = ws + (((N.depth - i) & 1) ? N.o_dzb : N.o_dza);
       GemmOp op = gemm_op(N.M, N.width, out);
@@ -428,13 +496,16 @@ int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_dsk_r, co
       op.C = dz_prev;
       op.c_si = N.width;
       op.c_sj = 1;
-      if (int rc = launch_gemm(op, "joint_mlp_da_gemm", st)) return rc;
-      dz = dz_prev;
+      ops[n_ops++] = op;
+      dz_next = dz_prev;
     }
+    // the three products only read dZ of this layer: one launch
+    if (int rc = launch_gemms(ops, n_ops, "joint_mlp_bwd_gemms", st)) return rc;
+    dz = dz_next;
   }
   if (dL_djoints) {
     ProfScope prof_("joint_encode_bwd_kernel", st);
-    joint_encode_bwd_kernel<<<(N.M * 3 + 63) / 64, 64, 0, st>>>(N.M, net->degree_p, N.enc, x0, N.x0_users,
+    joint_encode_bwd_kernel<<<(N.M * 3 * 32 + 127) / 128, 128, 0, st>>>(N.M, net->degree_p, N.enc, x0, N.x0_users,
                                                                 ws + N.o_dx0, (long long)N.M * N.enc, dL_djoints);
     SKGS_CHECK_LAUNCH("joint_encode_bwd_kernel");
   }

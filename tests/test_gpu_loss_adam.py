@@ -231,7 +231,7 @@ def test_train_iteration_matches_autograd_plus_torch_adam(graph):
     before = {k: hp.params[k].detach().clone() for k in loop.names}
     losses = []
     if graph:
-        loop.capture(0, target)
+        loop.capture(0, target, headroom=4.0)
         for k in loop.names:  # capture leaves parameters and moments untouched
             assert torch.equal(hp.params[k], before[k]) and float(loop.exp_avg[k].abs().max()) == 0.0
         for _ in range(n):

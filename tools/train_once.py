@@ -7,7 +7,7 @@ from sk_gs_b200.pipeline import HotPath
 from sk_gs_b200.train import TrainLoop
 
 cfg = S.CONFIGS['c2']
-hp = HotPath(S.make_scene(cfg, views=1), 'cuda:0', requires_grad=False, merged_sh=True)
+hp = HotPath(S.make_scene(cfg, views=1), 'cuda:0', requires_grad=False, merged_sh=True, joint_mlp=True, head_std=0.02)
 loop = TrainLoop(hp)
 with torch.no_grad():
     target = hp.render(0)['images'].detach().clone()
