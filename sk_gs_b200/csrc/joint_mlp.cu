@@ -19,13 +19,20 @@ namespace skgs {
 namespace {
 
 constexpr int GM_TI = 32;                    // rows of C per CTA: one per lane
-constexpr int GM_WARPS = 4;
-constexpr int GM_JW = 2;                     // columns of C per warp
+#ifndef SKGS_GM_WARPS
+#define SKGS_GM_WARPS 4
+#endif
+#ifndef SKGS_GM_JW
+#define SKGS_GM_JW 2
+#endif
+constexpr int GM_WARPS = SKGS_GM_WARPS;
+constexpr int GM_JW = SKGS_GM_JW;            // columns of C per warp
 constexpr int GM_TJ = GM_WARPS * GM_JW;      // columns of C per CTA
 constexpr int GM_RC = 128;                   // reduction chunk staged in shared memory
 constexpr int GM_LD = GM_RC + 4;             // row stride: 16-byte aligned rows, conflict-free 128-bit loads
 constexpr int GM_THREADS = GM_WARPS * 32;
 constexpr int MAX_X0_USERS = 8;
+static_assert((GM_TI * GM_RC) % GM_THREADS == 0 && (GM_TJ * GM_RC) % GM_THREADS == 0, "whole loads per thread");
 
 // C(i,j) = epilogue( sum_r A(i,r) * B(j,r) ),  i < I, j < J, r < R; every operand is addressed through element strides.
 struct GemmOp {

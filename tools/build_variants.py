@@ -11,6 +11,9 @@ VARIANTS = {
     'rslots4': ['-DSKGS_RSLOTS=4'],
     'os8': ['-DSKGS_OS_ITEMS=8'],
     'os24': ['-DSKGS_OS_ITEMS=24'],
+    'gw8j1': ['-DSKGS_GM_WARPS=8', '-DSKGS_GM_JW=1'],
+    'gw8j2': ['-DSKGS_GM_WARPS=8', '-DSKGS_GM_JW=2'],
+    'gw4j1': ['-DSKGS_GM_WARPS=4', '-DSKGS_GM_JW=1'],
     'adilp4': ['-DSKGS_AD_ILP=4', '-DSKGS_AD_MINB=2'],
     'adilp1': ['-DSKGS_AD_ILP=1', '-DSKGS_AD_MINB=8'],
     'adilp2b8': ['-DSKGS_AD_ILP=2', '-DSKGS_AD_MINB=6'],
