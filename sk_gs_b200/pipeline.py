@@ -2,9 +2,10 @@
 
 Mirrors what `SkeletonGaussianSplatting.render` does per view in the `sk` stage
 (/root/reference/networks/sk_gs.py:1206-1242 -> forward :1160-1204 -> sk_stage :1109-1150 -> render_gs_offical),
-minus the joint MLP.  The two steps that follow the path in a training iteration - photometric loss
-(8f-2, networks/sk_gs.py:1524-1529) and Adam (8f-3, networks/gaussian_splatting.py:445-453) - are optional stages of
-`step_grads` / `TrainLoop`; the benchmarked metric (BASELINE.json) excludes them."""
+with the joint rotations as leaf parameters by default.  The step before the path (joint-rotation network, SURVEY.md 8f-1,
+`joint_mlp=True`) and the two steps after it - photometric loss (8f-2, networks/sk_gs.py:1524-1529) and Adam (8f-3,
+networks/gaussian_splatting.py:445-453) - are optional stages of `step_grads` / `sk_gs_b200.train.TrainLoop`; the
+benchmarked metric (BASELINE.json) excludes them."""
 from __future__ import annotations
 
 from dataclasses import dataclass
