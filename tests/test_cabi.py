@@ -95,3 +95,47 @@ def test_cpu_tensors_fail_loudly():
                               scales=sc.scaling.exp(), rotations=sc.rotation)
     with pytest.raises(RuntimeError, match='no CPU path'):
         fk_lbs(sc.xyz, sc.joints, sc.sk_r, sc.sk_d_rot, sc.sk_d_scale, sc.g_tr, sc.parents, sc.root, sp_W=sc.sp_W)
+
+
+def test_widening_entry_points_validate_arguments_before_any_device_work():
+    """skgs_image_loss / skgs_adam_step / skgs_joint_mlp_*: bad arguments return SKGS_ERR_INVALID_ARG with a message."""
+    L = _lib.lib()
+    assert L.skgs_image_loss_workspace_bytes(800, 800) >= 9 * 800 * 800 * 4
+    assert L.skgs_image_loss(0, 10, *([None] * 2), 0, 0, 1.0, 1.0, 1.0, *([None] * 4)) == -1
+    assert b'empty image' in L.skgs_last_error()
+    assert L.skgs_image_loss(8, 8, *([None] * 2), 0, 0, 1.0, 1.0, 1.0, *([None] * 4)) == -1
+    assert b'null pointer' in L.skgs_last_error()
+    assert L.skgs_image_loss(8, 8, 1, 1, 5, 0, 1.0, 1.0, 1.0, 1, 1, None, None) == -1
+    assert b'target_pixel_stride' in L.skgs_last_error()
+    assert L.skgs_image_loss(8, 8, 1, 1, 3, 7, 1.0, 1.0, 1.0, 1, 1, None, None) == -1
+    assert b'method' in L.skgs_last_error()
+
+    table = (_lib.AdamTensor * 1)()
+    assert L.skgs_adam_step(table, 17, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'count 17' in L.skgs_last_error()
+    assert L.skgs_adam_step(table, 1, 0, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'step must be >= 1' in L.skgs_last_error()
+    assert L.skgs_adam_step(table, 1, 1, 1.5, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'hyper-parameters' in L.skgs_last_error()
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == 0  # numel 0: nothing to do
+    table[0] = _lib.AdamTensor(None, None, None, None, 8, 1e-3, 1e-3, 0, 0, 0, 0, None)
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'null pointer' in L.skgs_last_error()
+    table[0] = _lib.AdamTensor(1, 1, 1, 1, 8, 1e-3, 1e-3, 4, 4, 0, 0, None)
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'split < period' in L.skgs_last_error()
+    table[0] = _lib.AdamTensor(1, 1, 1, 1, 8, 1e-3, 1e-3, 0, 0, 4, 5, 1)
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert b'compact gradient' in L.skgs_last_error()
+
+    net = _lib.JointMlp(32, 10, 6, 256, 8, 1 << 4, 11, 1, None)
+    tot = C.c_int64()
+    assert L.skgs_joint_mlp_layout(C.byref(net), None, None, None, C.byref(tot)) == 0 and tot.value == 502539
+    assert L.skgs_joint_mlp_workspace_bytes(C.byref(net)) > 8 * 32 * 256 * 4
+    assert L.skgs_joint_mlp_forward(C.byref(net), *([None] * 7)) == -1  # theta == NULL
+    assert b'null pointer' in L.skgs_last_error()
+    bad = _lib.JointMlp(32, 10, 6, 256, 8, 1 << 4, 12, 1, None)
+    assert L.skgs_joint_mlp_layout(C.byref(bad), None, None, None, C.byref(tot)) == -1
+    assert b'11 outputs' in L.skgs_last_error()
+    assert L.skgs_joint_mlp_workspace_bytes(C.byref(bad)) == 0
+    assert L.skgs_joint_mlp_layout(None, None, None, None, None) == -1
