@@ -19,7 +19,7 @@ that detail.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 from torch import Tensor

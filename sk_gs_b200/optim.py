@@ -8,7 +8,6 @@ No CPU path: CPU parameters raise.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, List, Optional, Sequence
 
 import torch

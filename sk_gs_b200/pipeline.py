@@ -8,8 +8,7 @@ networks/gaussian_splatting.py:445-453) - are optional stages of `step_grads` / 
 benchmarked metric (BASELINE.json) excludes them."""
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 from torch import Tensor

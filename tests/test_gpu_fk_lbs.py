@@ -2,7 +2,6 @@
 
 Tolerances (fp32): forward 2e-6 abs on O(1) quantities; gradients 1e-4 relative to each tensor's largest magnitude.
 KNN indices must agree exactly (synthetic joints are generic: no exact distance ties)."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,7 +1,6 @@
 """Full BASELINE.json sizes on the GPU, checked through size-independent properties (the oracle would take too long):
 sortedness and consistency of the binning products, determinism, exact homogeneity of the backward in the upstream
 gradient, range checks - plus the B2 (in-tree API) entry points against B1."""
-import numpy as np
 import pytest
 import torch
 

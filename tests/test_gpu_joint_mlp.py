@@ -10,7 +10,7 @@ import torch
 
 from oracle import deform_net as OD
 from sk_gs_b200 import scene as S
-from sk_gs_b200.deform_net import (HEADS, NetConfig, SimpleDeformationNetwork, joint_mlp_backward_raw,
+from sk_gs_b200.deform_net import (NetConfig, SimpleDeformationNetwork, joint_mlp_backward_raw,
                                    joint_mlp_forward_raw)
 from sk_gs_b200.pipeline import HotPath
 from sk_gs_b200.train import TrainLoop

@@ -2,7 +2,6 @@
 autograd.  Used only to check the hand-derived backward formulas of the C oracle (tests/test_oracle_selfcheck.py).
 Small scenes only: it materialises [pixels, Gaussians] tensors.  Discrete decisions (culling, radius, tile rects) are
 taken from float64 arithmetic of the same formulas."""
-import math
 
 import torch
 

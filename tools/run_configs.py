@@ -2,7 +2,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from sk_gs_b200 import scene as S, _lib
+from sk_gs_b200 import scene as S
 from sk_gs_b200 import diff_gaussian_rasterization as DGR
 from sk_gs_b200.pipeline import HotPath
 names = sys.argv[1:] or ['c1', 'c2', 'c3', 'c4', 'ns', 'c5']
