@@ -139,3 +139,22 @@ def test_widening_entry_points_validate_arguments_before_any_device_work():
     assert b'11 outputs' in L.skgs_last_error()
     assert L.skgs_joint_mlp_workspace_bytes(C.byref(bad)) == 0
     assert L.skgs_joint_mlp_layout(None, None, None, None, None) == -1
+
+
+def test_sass_carries_the_instructions_the_design_relies_on():
+    """Evidence that the shipped binary is the design DESIGN.md describes (no GPU needed, cuobjdump on the in-tree .so):
+    NVLS in-switch reduction (multimem.ld_reduce -> LDGMC...ADD.F32x4, multimem.st -> STG.E.128...MMIO), one 16-byte
+    vector RED per gradient group in the compositing backward, match.any ranking in the onesweep sort, and nothing
+    compiled for an architecture other than sm_100a."""
+    import subprocess
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert len(re.findall(r'LDGMC\.E\.ADD\.F32x4', sass)) >= 4            # allreduce_mm.cu
+    assert 'STG.E.128.STRONG.SYS.MMIO' in sass                            # multimem.st of the reduced slice
+    assert len(re.findall(r'REDG\.E\.ADD\.F32x4', sass)) >= 3             # composite.cu flush_slots: 3 x red.v4.f32
+    assert 'MATCH.ANY' in sass                                            # raster_fwd.cu onesweep ranking
+    assert 'REDG.E.ADD.F64' in sass                                       # image_loss.cu loss sums
+    funcs = set(re.findall(r'Function : (\S+)', sass))
+    for name in ('composite_fwd_kernel', 'composite_bwd_kernel', 'onesweep_pass_kernel', 'preprocess_scan_kernel',
+                 'fk_lbs_fwd_kernel', 'lbs_bwd_jm_kernel', 'multimem_allreduce_kernel', 'ssim_stats_kernel',
+                 'ssim_grad_kernel', 'adam_kernel', 'small_gemm_kernel'):
+        assert any(name in f for f in funcs), name
