@@ -74,8 +74,7 @@ typedef struct skgs_raster_settings {
   int32_t sh_degree;        /* active degree D, 0..3 */
   int32_t quat_wxyz;        /* 1: rotations are (w,x,y,z) (upstream boundary B1); 0: (x,y,z,w) (in-tree boundary B2) */
   int32_t prefiltered;      /* accepted for API parity; culled points are simply skipped */
-  int32_t debug;            /* bit 0: accepted for API parity; bit 1: stop after binning (tests);
-                               bit 3: use the experimental tile-bucketed binning instead of duplicate + onesweep */
+  int32_t debug;            /* bit 0: accepted for API parity; bit 1: stop after binning (tests) */
   const float* viewmatrix;  /* device [16] */
   const float* projmatrix;  /* device [16] */
   const float* campos;      /* device [3] */
@@ -93,47 +92,56 @@ typedef struct skgs_raster_layout {
   size_t cov3D;          /* float  [P][6] */
   size_t conic_opacity;  /* float4 [P]   (conic a, b, c, opacity) */
   size_t rgbd;           /* float4 [P]   (r, g, b, depth) */
+  size_t cull;           /* float4 [P]   footprint-culling record of the compositing kernels: (pmin, -B/C, -B/A, -) with
+                                         pmin = -log(255 opacity) - margin, the exponent below which alpha < 1/255 */
   size_t clamped;        /* uint8  [P]   bit c set <=> colour channel c was clamped at 0 */
   size_t tiles_touched;  /* uint32 [P] */
   size_t point_offsets;  /* uint32 [P]   inclusive prefix sum of tiles_touched */
   size_t scan_state;     /* uint64 [ceil(P/256)+1] look-back words of the fused scan */
-  size_t tile_count;     /* uint32 [tiles]  list length of every tile (counted in preprocess, bucketed binning) */
-  size_t tile_cursor;    /* uint32 [tiles]  running write cursor of every tile's bucket */
-  size_t geom_grads;     /* float  [P][12] packed backward accumulators: mean2D.xy conic.abc opacity depth - rgb - */
-  /* binning (capacity R_cap entries) */
-  size_t keys_unsorted;  /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */
-  size_t vals_unsorted;  /* uint32 [R_cap] */
-  size_t keys_sorted;    /* uint64 [R_cap] */
-  size_t point_list;     /* uint32 [R_cap]  Gaussian ids sorted by (tile, depth), stable */
+  size_t geom_grads;     /* float  [P][12] packed backward accumulators: mean2D.xy conic.abc opacity depth - rgb -
+                                         (zero outside the composite-bwd -> preprocess-bwd window) */
+  /* binning (capacity R_cap entries): two physical key/value buffers the radix passes ping-pong between */
+  size_t keys_a;         /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */
+  size_t vals_a;         /* uint32 [R_cap]  Gaussian ids, emission order */
+  size_t keys_b;         /* uint64 [R_cap] */
+  size_t vals_b;         /* uint32 [R_cap] */
   size_t sort_hist;      /* uint32 [8][256] digit histograms */
-  size_t sort_status;    /* uint32 [passes][tiles_of_keys][256] look-back words + tickets */
+  size_t sort_status;    /* uint32 [tiles_of_keys][256] look-back words (tagged by pass) */
   /* img */
-  size_t ranges;         /* uint2  [tiles] */
+  size_t ranges;         /* uint2  [tiles]  [start, end) of every screen tile in the sorted list, (0, 0) if empty */
   size_t n_contrib;      /* uint32 [H*W] */
   size_t final_T;        /* float  [H*W] */
   size_t tile_order;     /* uint32 [tiles]  tiles by decreasing list length (work order of the compositing kernels) */
   size_t work_counters;  /* uint32 [2]      work tickets of the forward / backward compositing kernels */
 } skgs_raster_layout;
 
-/* Lives at geom + layout.header; written on the device, never read by the library on the host. */
+/* Lives at geom + layout.header; written on the device, never read by the library on the host.
+ * After the forward the lists sorted by (tile, depth) - stable, identical to cub::DeviceRadixSort::SortPairs on the
+ * low 32 + getHigherMsb(tiles) key bits (reference gaussian_rasterizer_forward.cu:224-229) - are keys_a / vals_a if
+ * final_buf == 0, keys_b / vals_b if final_buf == 1: a radix pass whose digit is the same for every key (typically the
+ * sign / exponent byte of the depth) is skipped on the device, so the parity of executed passes is data dependent. */
 typedef struct skgs_raster_header {
   uint32_t num_rendered;  /* R = sum tiles_touched (may exceed R_cap) */
   uint32_t num_visible;   /* Gaussians with radius > 0 */
   uint32_t scan_ticket;   /* internal */
   uint32_t overflow;      /* 1 if R > R_cap: the image of this call is INVALID, re-run with a larger binning arena */
   uint32_t sort_ticket[8]; /* internal */
-  uint32_t reserved[4];
+  uint32_t sort_plan[8];  /* per radix pass: bit 0 = skipped, bit 1 = source buffer (0: a, 1: b) */
+  uint32_t final_buf;     /* buffer that holds the sorted lists: 0 = keys_a / vals_a, 1 = keys_b / vals_b */
+  uint32_t emit_done;     /* internal */
+  uint32_t reserved[10];
 } skgs_raster_header;
 
 SKGS_API int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skgs_raster_layout* out);
 
-/* Forward: preprocess (+fused prefix sum) -> duplicate-with-keys (+digit histograms) -> onesweep radix sort ->
- * tile ranges -> per-tile compositing.  Exactly one of shs / colors_precomp and one of (scales, rotations) /
- * cov3D_precomp must be non-NULL (same rule as networks/renderer/gaussian_render.py:250-255).
+/* Forward: preprocess (+ fused prefix sum + key emission with all digit histograms, ONE kernel) -> onesweep radix sort
+ * (constant digits skipped on the device, the last pass writes the tile ranges) -> tile order -> per-tile compositing.
+ * Exactly one of shs / colors_precomp and one of (scales, rotations) / cov3D_precomp must be non-NULL (same rule as
+ * networks/renderer/gaussian_render.py:250-255).
  *   means3D [P][3], shs [P][M][3], colors_precomp [P][3], opacities [P], scales [P][3], rotations [P][4], cov3D_precomp [P][6]
  *   out_color [3][H][W], out_depth [H][W], out_alpha [H][W] (= 1 - T), radii int32 [P]
  *   num_rendered_host: optional PINNED host uint32[4] that receives the first four header words
- *   {R, num_visible, -, overflow} by an async copy enqueued after the scan and again after key emission.
+ *   {R, num_visible, -, overflow} by an async copy enqueued right after the preprocess kernel.
  * P == 0 is legal (image = background). */
 SKGS_API int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
                                  const float* shs, const float* colors_precomp, const float* opacities,
@@ -141,16 +149,22 @@ SKGS_API int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32
                                  void* binning, int64_t R_cap, void* img, float* out_color, float* out_depth,
                                  float* out_alpha, int32_t* radii, uint32_t* num_rendered_host, void* stream);
 
-/* Forward split in two for callers that want R before sizing the binning arena:
- *   _geometry: preprocess + scan (+ async copy of the header words to num_rendered_host)
- *   _render  : duplicate + sort + ranges + composite, for the R_cap the binning arena was sized for.          */
+/* Forward split in two, for callers that look at R between the stages (the reference sizes its binning buffer from a
+ * blocking read of R, gaussian_rasterizer_forward.cu:208-213):
+ *   _geometry: preprocess + scan (+ async copy of the header words to num_rendered_host).  With a binning arena
+ *              (binning != NULL, sized for R_cap entries, plus the img arena) the same kernel also emits the keys;
+ *              with binning == NULL nothing is emitted and R_cap / img are ignored.
+ *   _render  : [key emission from the stored geometry unless keys_emitted] + sort + ranges + composite, for the R_cap
+ *              the binning arena was sized for.  May be re-run on the same geometry with a larger arena
+ *              (keys_emitted = 0) after an overflow. */
 SKGS_API int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
                                           const float* shs, const float* colors_precomp, const float* opacities,
                                           const float* scales, const float* rotations, const float* cov3D_precomp,
-                                          void* geom, int32_t* radii, uint32_t* num_rendered_host, void* stream);
+                                          void* geom, int32_t* radii, void* binning, int64_t R_cap, void* img,
+                                          uint32_t* num_rendered_host, void* stream);
 SKGS_API int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning,
                                         int64_t R_cap, int64_t R_hint, void* img, const int32_t* radii,
-                                        float* out_color, float* out_depth, float* out_alpha,
+                                        int32_t keys_emitted, float* out_color, float* out_depth, float* out_alpha,
                                         uint32_t* num_rendered_host, void* stream);
 
 /* Backward.  dL_dcolor [3][H][W] is required; dL_ddepth / dL_dalpha [H][W] may be NULL.
@@ -256,7 +270,10 @@ SKGS_API int skgs_image_loss(int32_t H, int32_t W, const float* image, const flo
  * `dynamic_hyper` (device float[1 + 2 count], may be NULL) = {sqrt(1 - beta2^step), then per tensor lr_i / (1 - beta1^step)
  * and lr2_i / (1 - beta1^step)}: when
  * given it overrides `step` and `lr`, so that a captured CUDA graph can be replayed with the values of the current
- * iteration (uploaded by the caller) instead of the ones frozen at capture time. */
+ * iteration (uploaded by the caller) instead of the ones frozen at capture time.
+ * `skip_if_nonzero` (device uint32, may be NULL): when the word is non-zero at execution time the whole step is a no-op.
+ * Point it at skgs_raster_header.overflow of the render that produced the gradients: a fixed-capacity (CUDA-graph) render
+ * whose binning arena overflowed yields an invalid image and invalid gradients, which must not reach the parameters. */
 #define SKGS_ADAM_MAX_TENSORS 16
 typedef struct skgs_adam_tensor {
   float* param;
@@ -277,7 +294,7 @@ typedef struct skgs_adam_tensor {
 } skgs_adam_tensor;
 SKGS_API int skgs_adam_step(const skgs_adam_tensor* tensors /* host */, int32_t count, int32_t step, double beta1,
                             double beta2, double eps, float grad_scale, const float* dynamic_hyper,
-                            void* stream);
+                            const uint32_t* skip_if_nonzero, void* stream);
 
 /* Joint-rotation network of the `sk` stage, the step before forward kinematics:
  * joints [M,3], time t -> sk_r [M,4] (unit quaternion xyzw), d_rot [M,4], d_scale [M,3].
@@ -319,6 +336,13 @@ SKGS_API int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_
  * rank-th slice with multimem.ld_reduce / multimem.st.  The caller brackets the call with cross-GPU barriers on the
  * same stream.  The reference has no counterpart (its DDP wiring is unused, my_ext/framework.py:339-357). */
 SKGS_API int skgs_multimem_allreduce(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world, void* stream);
+
+/* Multi-view steps: the reference loops over the views of a step and autograd SUMS their gradients
+ * (networks/sk_gs.py:1220); the MAX of the screen radii over the views feeds max-radius tracking
+ * (networks/gaussian_splatting.py:638-640).  dst[i] += src[i] over a flat fp32 arena (both 16-byte aligned) and
+ * dst[i] = max(dst[i], src[i]) over int32 radii. */
+SKGS_API int skgs_accumulate_f32(float* dst, const float* src, int64_t numel, void* stream);
+SKGS_API int skgs_max_i32(int32_t* dst, const int32_t* src, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

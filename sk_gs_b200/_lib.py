@@ -24,14 +24,20 @@ class RasterSettings(C.Structure):
 
 
 _LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
-                  'rgbd', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'tile_count', 'tile_cursor', 'geom_grads',
-                  'keys_unsorted',
-                  'vals_unsorted', 'keys_sorted', 'point_list', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
+                  'rgbd', 'cull', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads',
+                  'keys_a', 'vals_a', 'keys_b', 'vals_b', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
                   'final_T', 'tile_order', 'work_counters']
 
 
 class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in _LAYOUT_FIELDS]
+
+
+class RasterHeader(C.Structure):
+    """struct skgs_raster_header (lives at geom + layout.header)."""
+    _fields_ = [('num_rendered', C.c_uint32), ('num_visible', C.c_uint32), ('scan_ticket', C.c_uint32),
+                ('overflow', C.c_uint32), ('sort_ticket', C.c_uint32 * 8), ('sort_plan', C.c_uint32 * 8),
+                ('final_buf', C.c_uint32), ('emit_done', C.c_uint32), ('reserved', C.c_uint32 * 10)]
 
 
 class Skeleton(C.Structure):
@@ -58,6 +64,7 @@ class JointMlp(C.Structure):
     ]
 
 
+ABI_VERSION = 2  # must equal skgs_abi_version() of the loaded library
 ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
 
@@ -73,8 +80,10 @@ _SIGNATURES = {
     'skgs_raster_layout_query': (C.c_int, [_i32, _i32, _i32, _i64, C.POINTER(RasterLayout)]),
     'skgs_raster_forward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 8 + [_vp, _i64, _vp] +
                             [_vp] * 6),
-    'skgs_raster_forward_geometry': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp] * 4),
-    'skgs_raster_forward_render': (C.c_int, [C.POINTER(RasterSettings), _i32, _vp, _vp, _i64, _i64, _vp] + [_vp] * 6),
+    'skgs_raster_forward_geometry': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 +
+                                     [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'skgs_raster_forward_render': (C.c_int, [C.POINTER(RasterSettings), _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i32] +
+                                   [_vp] * 5),
     'skgs_raster_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp, _vp, _i64, _vp] +
                              [_vp] * 12),
     'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 8),
@@ -86,13 +95,15 @@ _SIGNATURES = {
     'skgs_image_loss': (C.c_int, [_i32, _i32, _vp, _vp, _i32, _i32, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp,
                                   _vp]),
     'skgs_adam_step': (C.c_int, [C.POINTER(AdamTensor), _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_float,
-                                 _vp, _vp]),
+                                 _vp, _vp, _vp]),
     'skgs_joint_mlp_layout': (C.c_int, [C.POINTER(JointMlp), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     'skgs_joint_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(JointMlp)]),
     'skgs_joint_mlp_forward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_joint_mlp_backward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
+    'skgs_accumulate_f32': (C.c_int, [_vp, _vp, _i64, _vp]),
+    'skgs_max_i32': (C.c_int, [_vp, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -109,6 +120,9 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
+        if L.skgs_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'{LIB_PATH} has ABI version {L.skgs_abi_version()}, this package needs {ABI_VERSION}: '
+                               f'rebuild it (python __graft_entry__.py)')
         _lib = L
     return _lib
 
@@ -116,7 +130,7 @@ def lib():
 def check_exports():
     """Load the library and verify every declared symbol is exported (no compute call; works without a GPU)."""
     L = lib()
-    assert L.skgs_abi_version() == 1
+    assert L.skgs_abi_version() == ABI_VERSION
     assert L.skgs_built_for_sm() == 100
     return sorted(_SIGNATURES)
 

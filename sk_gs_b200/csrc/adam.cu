@@ -30,6 +30,7 @@ struct AdamArgs {
   int block_start[SKGS_ADAM_MAX_TENSORS + 1];
   int slot[SKGS_ADAM_MAX_TENSORS];         // index in the caller's table (empty tensors are dropped)
   const float* dyn;                        // optional device table {bc2_sqrt, (step_size, step_size2)[...]}
+  const uint32_t* skip;                    // optional device flag: non-zero -> the whole step is a no-op
   int count;
   float w1;         // 1 - beta1
   float beta2;
@@ -152,6 +153,8 @@ __device__ __forceinline__ void adam_chunk(const skgs_adam_tensor& T, const Hype
 }
 
 __global__ void __launch_bounds__(AD_THREADS, SKGS_AD_MINB) adam_kernel(const __grid_constant__ AdamArgs a) {
+  // the gradients of a render whose binning arena overflowed are garbage: leave parameters and moments untouched
+  if (a.skip != nullptr && __ldg(a.skip) != 0u) return;
   int ti = 0;
   while (ti + 1 < a.count && (int)blockIdx.x >= a.block_start[ti + 1]) ++ti;
   const skgs_adam_tensor& T = a.t[ti];
@@ -180,7 +183,7 @@ using namespace skgs;
 
 extern "C" int skgs_adam_step(const skgs_adam_tensor* tensors, int32_t count, int32_t step, double beta1,
                               double beta2, double eps, float grad_scale, const float* dynamic_hyper,
-                              void* stream) {
+                              const uint32_t* skip_if_nonzero, void* stream) {
   SKGS_CHECK_ARG(count >= 0 && count <= SKGS_ADAM_MAX_TENSORS, "adam_step: count %d outside [0, %d]", count,
                  SKGS_ADAM_MAX_TENSORS);
   SKGS_CHECK_ARG(count == 0 || tensors, "adam_step: null tensor table");
@@ -219,6 +222,7 @@ extern "C" int skgs_adam_step(const skgs_adam_tensor* tensors, int32_t count, in
   a.eps = (float)eps;
   a.grad_scale = grad_scale;
   a.dyn = dynamic_hyper;
+  a.skip = skip_if_nonzero;
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope prof_("adam_kernel", st);

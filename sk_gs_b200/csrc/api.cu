@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -23,6 +24,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SKGS_PDL");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
 
 // ---- optional per-kernel timing -------------------------------------------------------------------------------
 struct ProfRec {
@@ -105,7 +115,7 @@ using namespace skgs;
 extern "C" {
 
 const char* skgs_last_error(void) { return g_err; }
-int skgs_abi_version(void) { return 1; }
+int skgs_abi_version(void) { return 2; }
 int skgs_built_for_sm(void) { return 100; }
 uint64_t skgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -167,36 +177,27 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   // ---- geom (header + scan_state first: they are reset by one memset per forward)
   out->header = take(sizeof(skgs_raster_header));
   out->scan_state = take(((Pz + 255) / 256 + 1) * sizeof(uint64_t));
-  {
-    const size_t ntiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    out->tile_count = take(ntiles * 4);   // zeroed together with header + scan_state
-    out->tile_cursor = take(ntiles * 4);
-  }
   out->means2D = take(Pz * 8);
   out->depths = take(Pz * 4);
   out->cov3D = take(Pz * 24);
   out->conic_opacity = take(Pz * 16);
   out->rgbd = take(Pz * 16);
+  out->cull = take(Pz * 16);
   out->clamped = take(Pz);
   out->tiles_touched = take(Pz * 4);
   out->point_offsets = take(Pz * 4);
   out->geom_grads = take(Pz * 48);
   out->geom_bytes = o;
-  // ---- binning
+  // ---- binning: two physical key/value buffers; keys are emitted into a, the executed radix passes alternate
+  //      a -> b -> a ...; header.final_buf names the buffer that holds the sorted lists (data dependent: passes whose
+  //      digit is constant are skipped on the device)
   o = 0;
   const size_t Rz = (size_t)R_cap;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const int passes = sort_passes(gx, gy);
-  const size_t kA = take(Rz * 8), vA = take(Rz * 4), kB = take(Rz * 8), vB = take(Rz * 4);
-  // keys are emitted into A; pass p writes to B, A, B, ...  The final result is in B for an odd number of passes and
-  // back in A for an even number: report the physical location of the FINAL lists as keys_sorted / point_list.
-  if (passes % 2 == 1) {
-    out->keys_unsorted = kA; out->vals_unsorted = vA; out->keys_sorted = kB; out->point_list = vB;
-  } else {
-    out->keys_unsorted = kA; out->vals_unsorted = vA; out->keys_sorted = kA; out->point_list = vA;
-  }
-  (void)kB;
-  (void)vB;
+  out->keys_a = take(Rz * 8);
+  out->vals_a = take(Rz * 4);
+  out->keys_b = take(Rz * 8);
+  out->vals_b = take(Rz * 4);
   out->sort_hist = take(8 * 256 * sizeof(uint32_t));
   out->sort_status = take(((Rz + OS_TILE_KEYS - 1) / OS_TILE_KEYS + 1) * 256 * sizeof(uint32_t));
   out->binning_bytes = o;
@@ -211,66 +212,52 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   return SKGS_OK;
 }
 
-// physical A/B buffers regardless of pass parity (internal)
-static void physical_buffers(const skgs_raster_layout& lay, int64_t R_cap, skgs_raster_layout& phys) {
-  phys = lay;
-  const size_t Rz = (size_t)R_cap;
-  size_t o = 0;
-  auto take = [&](size_t bytes) {
-    const size_t at = o;
-    o = align_up(o + bytes, ARENA_ALIGN);
-    return at;
-  };
-  phys.keys_unsorted = take(Rz * 8);
-  phys.vals_unsorted = take(Rz * 4);
-  phys.keys_sorted = take(Rz * 8);
-  phys.point_list = take(Rz * 4);
-}
-
 int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
                                  const float* shs, const float* colors_precomp, const float* opacities,
                                  const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
-                                 int32_t* radii, uint32_t* num_rendered_host, void* stream) {
+                                 int32_t* radii, void* binning, int64_t R_cap, void* img, uint32_t* num_rendered_host,
+                                 void* stream) {
   RasterParams rp;
   int rc = fill_params(s, P, M, rp);
   if (rc) return rc;
   rc = check_inputs(s, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
   if (rc) return rc;
   SKGS_CHECK_ARG(geom != nullptr && (P == 0 || radii != nullptr), "geom arena / radii is NULL");
+  SKGS_CHECK_ARG(binning == nullptr || (img != nullptr && R_cap > 0), "key emission needs the img arena and R_cap > 0");
   skgs_raster_layout lay;
-  rc = skgs_raster_layout_query(P, rp.W, rp.H, 0, &lay);
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, binning ? R_cap : 0, &lay);
   if (rc) return rc;
   return launch_preprocess_scan(rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                (char*)geom, lay, radii, num_rendered_host, (s->debug & 8) != 0, (cudaStream_t)stream);
+                                (char*)geom, lay, radii, num_rendered_host, (char*)binning, (char*)img,
+                                binning ? R_cap : 0, (cudaStream_t)stream);
 }
 
-int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning, int64_t R_cap,
-                               int64_t R_hint, void* img, const int32_t* radii, float* out_color, float* out_depth,
-                               float* out_alpha, uint32_t* num_rendered_host, void* stream) {
-  RasterParams rp;
-  int rc = fill_params(s, P, 0, rp);
-  if (rc) return rc;
+// binning (optionally with key emission from the stored geometry) + tile order + compositing
+static int render_stage(const skgs_raster_settings* s, const RasterParams& rp, void* geom, void* binning, int64_t R_cap,
+                        int64_t R_hint, void* img, const int32_t* radii, bool emit, float* out_color, float* out_depth,
+                        float* out_alpha, uint32_t* num_rendered_host, cudaStream_t st) {
   SKGS_CHECK_ARG(geom && img && out_color && out_depth && out_alpha, "NULL arena / output");
   SKGS_CHECK_ARG(R_cap == 0 || binning != nullptr, "binning arena is NULL");
-  skgs_raster_layout lay, phys;
-  rc = skgs_raster_layout_query(P, rp.W, rp.H, R_cap, &lay);
+  skgs_raster_layout lay;
+  int rc = skgs_raster_layout_query(rp.P, rp.W, rp.H, R_cap, &lay);
   if (rc) return rc;
-  physical_buffers(lay, R_cap, phys);
-  cudaStream_t st = (cudaStream_t)stream;
-  // reset the overflow flag and the sort tickets (the render stage may be re-run on the same geometry)
-  auto* hdr = reinterpret_cast<skgs_raster_header*>((char*)geom + lay.header);
-  SKGS_CUDA(cudaMemsetAsync(&hdr->overflow, 0, sizeof(uint32_t) * 9, st));
-  if (!(s->debug & 8)) {  // default: duplicate-with-keys + onesweep radix sort (the algorithm named in the spec)
-    rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, phys, radii, R_cap, R_hint, num_rendered_host, st);
-    if (rc) return rc;
-    rc = launch_tile_order(rp, (char*)img, lay, st);
-  } else {                // experimental: tile-bucketed binning (binning_bucket.cu), bit-identical output
-    rc = launch_binning_bucket(rp, (char*)geom, (char*)binning, (char*)img, lay, phys, radii, R_cap, true,
-                               num_rendered_host, st);
-  }
+  rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, lay, radii, R_cap, R_hint, emit, num_rendered_host,
+                      st);
+  if (rc) return rc;
+  rc = launch_tile_order(rp, (char*)img, lay, st);
   if (rc) return rc;
   if (s->debug & 2) return SKGS_OK;  // test hook: stop after binning
   return launch_composite_fwd(rp, (char*)geom, (char*)binning, (char*)img, lay, out_color, out_depth, out_alpha, st);
+}
+
+int skgs_raster_forward_render(const skgs_raster_settings* s, int32_t P, void* geom, void* binning, int64_t R_cap,
+                               int64_t R_hint, void* img, const int32_t* radii, int32_t keys_emitted, float* out_color,
+                               float* out_depth, float* out_alpha, uint32_t* num_rendered_host, void* stream) {
+  RasterParams rp;
+  int rc = fill_params(s, P, 0, rp);
+  if (rc) return rc;
+  return render_stage(s, rp, geom, binning, R_cap, R_hint, img, radii, keys_emitted == 0, out_color, out_depth,
+                      out_alpha, num_rendered_host, (cudaStream_t)stream);
 }
 
 int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
@@ -278,11 +265,23 @@ int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, con
                         const float* rotations, const float* cov3D_precomp, void* geom, void* binning, int64_t R_cap,
                         void* img, float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
                         uint32_t* num_rendered_host, void* stream) {
-  int rc = skgs_raster_forward_geometry(s, P, M, means3D, shs, colors_precomp, opacities, scales, rotations,
-                                        cov3D_precomp, geom, radii, nullptr, stream);
+  RasterParams rp;
+  int rc = fill_params(s, P, M, rp);
   if (rc) return rc;
-  return skgs_raster_forward_render(s, P, geom, binning, R_cap, 0, img, radii, out_color, out_depth, out_alpha,
-                                    num_rendered_host, stream);
+  rc = check_inputs(s, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(geom != nullptr && img != nullptr && (P == 0 || radii != nullptr), "geom / img arena / radii is NULL");
+  SKGS_CHECK_ARG(R_cap == 0 || binning != nullptr, "binning arena is NULL");
+  skgs_raster_layout lay;
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, R_cap, &lay);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // one kernel: preprocess + scan + key emission (the capacity is known up front)
+  rc = launch_preprocess_scan(rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                              (char*)geom, lay, radii, nullptr, (char*)binning, (char*)img, R_cap, st);
+  if (rc) return rc;
+  return render_stage(s, rp, geom, binning, R_cap, 0, img, radii, /*emit=*/false, out_color, out_depth, out_alpha,
+                      num_rendered_host, st);
 }
 
 int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
@@ -310,8 +309,9 @@ int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, co
   rc = launch_composite_bwd(rp, (char*)geom, (const char*)binning, (const char*)img, lay, dL_dcolor, dL_ddepth,
                             dL_dalpha, st);
   if (rc) return rc;
+  uint32_t* bwd_ticket = reinterpret_cast<uint32_t*>((char*)const_cast<void*>(img) + lay.work_counters) + 1;
   return launch_preprocess_bwd(rp, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, (char*)geom,
-                               lay, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
+                               lay, bwd_ticket, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
                                dL_drotations, dL_dcov3D, st);
 }
 

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/skgs_b200.h"
 
 namespace skgs {
@@ -63,6 +65,33 @@ struct ProfScope {
   } while (0)
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may begin launching while its stream
+// predecessor is still draining; it must execute pdl_wait() before touching ANY global memory (griddepcontrol.wait
+// returns once every prerequisite grid has completed and flushed), and it releases its own successor with
+// pdl_trigger().  Used on the 20-kernel chain of one training step, where every kernel boundary otherwise costs a full
+// launch latency inside the CUDA graph.  SKGS_PDL=0 in the environment turns the attribute off (plain stream order).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // skgs_exp: the fully specified exp for x <= 0 shared (as a specification) with the oracle's orc_exp():
@@ -137,12 +166,10 @@ struct RasterParams {
 int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                            const float* opacities, const float* scales, const float* rotations,
                            const float* cov3D_precomp, char* geom, const skgs_raster_layout& lay, int32_t* radii,
-                           uint32_t* num_rendered_host, bool count_tiles, cudaStream_t st);
+                           uint32_t* num_rendered_host, char* binning, char* img, int64_t R_cap, cudaStream_t st);
 int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
-                   const int32_t* radii, int64_t R_cap, int64_t R_hint, uint32_t* num_rendered_host, cudaStream_t st);
-int launch_binning_bucket(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
-                          const skgs_raster_layout& phys, const int32_t* radii, int64_t R_cap, bool write_keys,
-                          uint32_t* num_rendered_host, cudaStream_t st);
+                   const int32_t* radii, int64_t R_cap, int64_t R_hint, bool emit, uint32_t* num_rendered_host,
+                   cudaStream_t st);
 int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st);
 int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                          float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
@@ -151,8 +178,8 @@ int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning
                          const float* dL_dalpha, cudaStream_t st);
 int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
-                          const int32_t* radii, char* geom, const skgs_raster_layout& lay, float* dL_dmeans3D,
-                          float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity, float* dL_dscales,
-                          float* dL_drotations, float* dL_dcov3D, cudaStream_t st);
+                          const int32_t* radii, char* geom, const skgs_raster_layout& lay, uint32_t* bwd_ticket,
+                          float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
+                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, cudaStream_t st);
 
 }  // namespace skgs

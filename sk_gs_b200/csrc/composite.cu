@@ -1,23 +1,26 @@
 // composite.cu - per-tile alpha compositing, forward and backward, for sm_100a.
 //
-// Design (measured motivation in profiles/r1_composite_v1.md): the first version ran one CTA per 16x16 tile and was
-// latency / tail bound (42 % issue utilisation, SMs idle 40 % of the kernel because a few long tiles finish last).
-// This version is WARP-granular and persistent:
-//   * work item  = half a tile (16 x 8 pixels), one warp, 4 horizontally adjacent pixels per lane (row terms of the
-//                  exponent are shared by the 4 pixels, so a (pixel, Gaussian) pair costs 3 FP instructions);
+// Design (measured motivation: profiles/r1_composite_v1.txt -> r1_final_composite_onesweep.txt -> r2_*): one CTA per
+// 16x16 tile is latency / tail bound (42 % issue utilisation, SMs idle 40 % of the kernel because a few long tiles finish
+// last).  These kernels are WARP-granular and persistent:
+//   * work item  = 8 x 4 pixels of a tile (8 items per tile), one warp, ONE pixel per lane;
 //   * scheduling = a global ticket hands out work items in order of DEcreasing tile length (tile_order_kernel), so the
 //                  long tiles start first and the tail is made of short ones; no __syncthreads anywhere - a warp that
-//                  finishes (all its pixels saturated) immediately takes the next item;
-//   * staging    = 32 Gaussians per batch in the warp's own shared-memory slice, the NEXT batch is gathered into
-//                  registers while the current one is composited (the dependent point_list -> attribute gathers are
-//                  hidden behind ~2k cycles of math);
-//   * culling    = conservative exponent cut-off pmin = -log(255 o) - 1e-4 per Gaussian: pairs below it can never
-//                  reach alpha >= 1/255 and skip exp(); finished pixels are parked at x = +huge so they fail the same
-//                  single comparison;
-//   * backward   = per-lane sums over its 4 pixels, 5-step shuffle reduction, lane j keeps the totals of batch entry j,
-//                  and each lane flushes its entry with three 16-byte vector REDs (red.global.add.v4.f32) - one RED
-//                  set per (half tile, Gaussian) instead of the reference's 9-13 scalar atomics per (pixel, Gaussian)
-//                  (my_ext/_C/src/nerf/gaussian_render.cu:295-338).
+//                  finishes (all its pixels saturated) immediately takes the next item; the ticket, tile id and range of
+//                  the NEXT item are fetched while the current one is composited (three dependent L2 round trips off
+//                  the critical path);
+//   * staging    = 32 Gaussians per batch in the warp's own shared-memory slice; the point_list index of batch b+2 and
+//                  the attributes of batch b+1 are in flight while batch b is composited;
+//   * culling    = phase 1 of every batch, lane j <-> staged Gaussian j: can any pixel centre of the 8x4 footprint reach
+//                  power >= pmin (= -log(255 o) - margin, precomputed per Gaussian by preprocess together with the two
+//                  slopes -B/C, -B/A)?  The minimum of the convex quadratic over the box lies on one of the (at most
+//                  two) box faces that look at the Gaussian's centre: two clamped 1-D minimisations, no division.  Only
+//                  the ballot's set bits are visited by the serial loop; finished pixels are parked at x = +huge;
+//   * backward   = every lane parks 9 partial sums (5 moments of q = o G dL/dalpha, opacity, colour; 10 with a depth
+//                  cotangent) of up to 6 surviving Gaussians in padded shared-memory rows, the rows are summed two per
+//                  lane, lane s turns slot s into the conic / mean gradients and flushes it with three 16-byte vector
+//                  REDs (red.global.add.v4.f32): one RED set per (item, Gaussian) instead of the reference's 9-13 scalar
+//                  atomics per (pixel, Gaussian) (my_ext/_C/src/nerf/gaussian_render.cu:295-338).
 // Semantics: SURVEY.md App. A.6 / A.7 (reference gaussian_render.cu:16-112, 182-341 + bg / depth / alpha terms).
 // Every operation that decides WHICH pairs contribute uses the contraction-proof helpers of common.cuh.
 #include "common.cuh"
@@ -37,12 +40,16 @@ constexpr int CW_WARPS = SKGS_CW_WARPS;     // warps per CTA (independent worker
 constexpr int CW_THREADS = CW_WARPS * 32;
 constexpr int NGRAD = 12;                   // packed per-Gaussian accumulators: mx my ca cb | cc op z - | r g b -
 constexpr float PARKED = 1.0e18f;           // x coordinate of a finished pixel: its exponent is -inf
+constexpr uint32_t FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------------------------
-// tile order: tiles sorted by decreasing list length (coarse: 8 sub-steps per octave), one CTA
+// tile order: tiles sorted by decreasing list length (coarse: 8 sub-steps per octave), one CTA.  Also turns the
+// (min, max) accumulators the last radix pass left in `ranges` into the reference's [start, end) / (0, 0) form and
+// resets the two compositing tickets.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TO_THREADS = 1024;
 constexpr int TO_BINS = 8 * 33;
+constexpr uint32_t RANGE_UNSET = 0xffffffffu;
 
 __device__ __forceinline__ int length_bin(uint32_t len) {
   if (len == 0) return 0;
@@ -52,15 +59,21 @@ __device__ __forceinline__ int length_bin(uint32_t len) {
 }
 
 __global__ void __launch_bounds__(TO_THREADS)
-tile_order_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order,
+tile_order_kernel(uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order,
                   uint32_t* __restrict__ counters) {
   __shared__ uint32_t s_hist[TO_BINS];
   __shared__ uint32_t s_base[TO_BINS];
+  pdl_wait();
+  pdl_trigger();
   for (int k = threadIdx.x; k < TO_BINS; k += TO_THREADS) s_hist[k] = 0;
   if (threadIdx.x < 2) counters[threadIdx.x] = 0;  // work tickets of the forward / backward compositing kernels
   __syncthreads();
   for (int t = threadIdx.x; t < tiles; t += TO_THREADS) {
-    const uint2 r = ranges[t];
+    uint2 r = ranges[t];
+    if (r.x == RANGE_UNSET || r.y <= r.x) {  // tile without list entries (or a forward that bailed out on overflow)
+      r = make_uint2(0u, 0u);
+      ranges[t] = r;
+    }
     atomicAdd(&s_hist[length_bin(r.y - r.x)], 1u);
   }
   __syncthreads();
@@ -72,7 +85,7 @@ tile_order_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restr
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      const uint32_t t = __shfl_up_sync(FULL, incl, o);
       if (lane >= o) incl += t;
     }
     if (lane == 31) s_wsum[warp] = incl;
@@ -83,7 +96,7 @@ tile_order_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restr
   }
   __syncthreads();
   for (int t = threadIdx.x; t < tiles; t += TO_THREADS) {
-    const uint2 r = ranges[t];
+    const uint2 r = ranges[t];  // this thread's own write above
     const uint32_t p = atomicAdd(&s_base[length_bin(r.y - r.x)], 1u);
     order[p] = (uint32_t)t;
   }
@@ -98,78 +111,97 @@ struct Staged {
   float2 m;    // pixel-space mean
   float4 co;   // conic a, b, c, opacity
   float4 c;    // r, g, b, depth
+  float4 k;    // culling record: pmin, -B/C, -B/A, -
   uint32_t g;  // Gaussian id
 };
 
-__device__ __forceinline__ void gather_id(uint32_t g, const float2* __restrict__ means2D,
-                                          const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
-                                          Staged& s) {
-  s.g = g;
-  s.m = __ldg(means2D + g);
-  s.co = __ldg(conic_opacity + g);
-  s.c = __ldg(rgbd + g);
-}
+struct GeomIn {
+  const float2* means2D;
+  const float4* conic_opacity;
+  const float4* rgbd;
+  const float4* cull;
+};
 
-__device__ __forceinline__ void gather(const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
-                                       const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
-                                       uint32_t pos, Staged& s) {
-  gather_id(__ldg(point_list + pos), means2D, conic_opacity, rgbd, s);
+__device__ __forceinline__ void gather_id(uint32_t g, const GeomIn& G, Staged& s) {
+  s.g = g;
+  s.m = __ldg(G.means2D + g);
+  s.co = __ldg(G.conic_opacity + g);
+  s.c = __ldg(G.rgbd + g);
+  s.k = __ldg(G.cull + g);
 }
 
 // commit a gathered entry to the warp's staging slot: g0 = (gx, gy, A', B'), g1 = (C', opacity, pmin, id), c
+// with A' = -A/2, B' = -B, C' = -C/2 (exact scalings)
 __device__ __forceinline__ void commit(const Staged& s, float4* g0s, float4* g1s, float4* cs, int lane) {
-  // alpha = o*exp(power) >= 1/255 needs power >= -log(255 o): conservative cut-off (margin 1e-4); everything that
-  // passes it still takes the exact test on alpha
-  const float pmin = s.co.w >= (1.0f / 255.0f) ? (-__logf(255.0f * s.co.w) - 1e-4f) : 1.0f;
   g0s[lane] = make_float4(s.m.x, s.m.y, -0.5f * s.co.x, -s.co.y);
-  g1s[lane] = make_float4(-0.5f * s.co.z, s.co.w, pmin, __uint_as_float(s.g));
+  g1s[lane] = make_float4(-0.5f * s.co.z, s.co.w, s.k.x, __uint_as_float(s.g));
   cs[lane] = s.c;
 }
 
-// Conservative footprint test (phase 1 of every batch, one staged Gaussian per lane): can ANY pixel centre of the
-// rectangle [X0,X1] x [Y0,Y1] reach power >= pmin?  power = -f/2 with f = A dx^2 + 2 B dx dy + C dy^2 convex, so its
-// minimum over the box of offsets is 0 if the centre is inside, else attained on one of the four edges at the clamped
-// 1-D minimiser.  The margin covers the fp32 rounding of both this test and pair_power() (relative 1e-6 of the largest
-// term magnitude over the box), so a pair that passes the exact per-pixel test is never culled here.
-__device__ __forceinline__ bool footprint_may_hit(const float4 g0, const float4 g1, float X0, float X1, float Y0,
-                                                  float Y1) {
-  const float A = -2.0f * g0.z, B = -g0.w, C = -2.0f * g1.x, pmin = g1.z;
-  const float dxlo = g0.x - X1, dxhi = g0.x - X0, dylo = g0.y - Y1, dyhi = g0.y - Y0;
+// Conservative footprint test (phase 1 of every batch, one staged Gaussian per lane, from registers): can ANY pixel
+// centre of the rectangle [X0,X1] x [Y0,Y1] reach power >= pmin?  power = -f/2 with f = A dx^2 + 2 B dx dy + C dy^2
+// convex (d = centre - pixel), so its minimum over the box of offsets is 0 if the centre is inside; otherwise it lies
+// on a box face that looks at the centre - the x-face nearest to dx = 0 (if 0 is outside the dx range) or the y-face
+// nearest to dy = 0 - at the clamped 1-D minimiser dy* = (-B/C) dx resp. dx* = (-B/A) dy (every segment from a box
+// point to the centre leaves the box through one of those faces, and f decreases along it).  The margin covers the
+// fp32 rounding of both this test and pair_power() (relative 1e-6 of the largest term magnitude over the box), so a
+// pair that passes the exact per-pixel test is never culled here.  Non-positive-definite conics carry pmin = -inf.
+__device__ __forceinline__ bool footprint_may_hit(const Staged& s, float X0, float X1, float Y0, float Y1) {
+  const float A = s.co.x, B = s.co.y, C = s.co.z, pmin = s.k.x;
+  const float dxlo = s.m.x - X1, dxhi = s.m.x - X0, dylo = s.m.y - Y1, dyhi = s.m.y - Y0;
   const bool in_x = dxlo <= 0.f && dxhi >= 0.f, in_y = dylo <= 0.f && dyhi >= 0.f;
-  float fmin = 0.f;
-  if (!(in_x && in_y)) {
-    const float invC = 1.0f / C, invA = 1.0f / A;
-    float f = __int_as_float(0x7f800000);
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const float ex = e ? dxhi : dxlo;
-      const float yy = fminf(fmaxf(-B * ex * invC, dylo), dyhi);
-      f = fminf(f, A * ex * ex + 2.0f * B * ex * yy + C * yy * yy);
-      const float ey = e ? dyhi : dylo;
-      const float xx = fminf(fmaxf(-B * ey * invA, dxlo), dxhi);
-      f = fminf(f, A * xx * xx + 2.0f * B * xx * ey + C * ey * ey);
-    }
-    fmin = f;
-  }
+  const float ex = dxlo > 0.f ? dxlo : dxhi;  // x-face nearest to the centre (meaningful when !in_x)
+  const float ey = dylo > 0.f ? dylo : dyhi;
+  // face dx = ex
+  const float ty = fminf(fmaxf(s.k.y * ex, dylo), dyhi);
+  const float fxe = ex * (A * ex + 2.0f * B * ty) + C * ty * ty;
+  // face dy = ey
+  const float tx = fminf(fmaxf(s.k.z * ey, dxlo), dxhi);
+  const float fye = ey * (C * ey + 2.0f * B * tx) + A * tx * tx;
+  const float inf = __int_as_float(0x7f800000);
+  float fmin = fminf(in_x ? inf : fxe, in_y ? inf : fye);
+  if (in_x && in_y) fmin = 0.f;
   const float DX = fmaxf(fabsf(dxlo), fabsf(dxhi)), DY = fmaxf(fabsf(dylo), fabsf(dyhi));
   const float eps = 1e-6f * (fabsf(A) * DX * DX + 2.0f * fabsf(B) * DX * DY + fabsf(C) * DY * DY) + 1e-3f;
   return !(-0.5f * fmin < pmin - eps);  // NaN-safe: anything unordered is kept
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward.  Work item = 8 x 4 pixels (one pixel per lane), 8 items per tile.
+// work distribution: one ticket per item, the next item is claimed (and its tile / range loaded) one item ahead
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ITEM_W = 8, ITEM_H = 4, ITEMS_PER_TILE = (TILE / ITEM_W) * (TILE / ITEM_H);
-constexpr int RSLOTS = SKGS_RSLOTS, RVALS = 10, RSTRIDE = 33;  // backward reduction staging (see composite_bwd_kernel)
 
+struct Item {
+  uint32_t id;     // ticket (>= num_items: none)
+  int tile;
+  uint2 range;
+};
+
+__device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items, const uint32_t* __restrict__ order,
+                                           const uint2* __restrict__ ranges, int lane) {
+  Item it;
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(ticket, 1u);
+  it.id = __shfl_sync(FULL, t, 0);
+  it.tile = 0;
+  it.range = make_uint2(0u, 0u);
+  if (it.id < num_items) {
+    it.tile = (int)__ldg(order + it.id / ITEMS_PER_TILE);
+    it.range = ranges[it.tile];
+  }
+  return it;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CW_THREADS)
 composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
                      uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
-                     const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
-                     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
-                     const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
-                     float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
-                     unsigned long long* __restrict__ stats) {
+                     const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                     const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
+                     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                     uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
   __shared__ float4 s_g0[CW_WARPS][32];
   __shared__ float4 s_g1[CW_WARPS][32];
   __shared__ float4 s_c[CW_WARPS][32];
@@ -177,53 +209,49 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
   float4* g0s = s_g0[warp];
   float4* g1s = s_g1[warp];
   float4* cs = s_c[warp];
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t* __restrict__ point_list = hdr->final_buf ? vals_b : vals_a;
   const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
   const size_t HW = (size_t)H * W;
   const uint32_t num_items = (uint32_t)tiles * ITEMS_PER_TILE;
 
-  while (true) {
-    uint32_t item = 0;
-    if (lane == 0) item = atomicAdd(ticket, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= num_items) break;
-    const int tile = (int)order[item / ITEMS_PER_TILE];
-    const int sub = (int)(item % ITEMS_PER_TILE);
-    const int tx = tile % gx, ty = tile / gx;
+  Item nxt_item = claim_item(ticket, num_items, order, ranges, lane);
+  while (nxt_item.id < num_items) {
+    const Item it = nxt_item;
+    const int sub = (int)(it.id % ITEMS_PER_TILE);
+    const int tx = it.tile % gx, ty = it.tile / gx;
     const int X0 = tx * TILE + (sub & 1) * ITEM_W, Y0 = ty * TILE + (sub >> 1) * ITEM_H;
     const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pyf = (float)py;
     const float fx0 = (float)X0, fy0 = (float)Y0;
-    const uint2 range = ranges[tile];
+    const uint2 range = it.range;
     const int total = (int)(range.y - range.x);
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
     float pxf = inside ? (float)px : PARKED;
     uint32_t last = 0;
     bool live = inside;
-    unsigned long long t_start = 0;
-    uint32_t n_batches = 0, n_surv = 0, n_hit = 0;
-    if (stats) t_start = clock64();
     // two-stage prefetch: the point_list index of batch b+2 and the attributes of batch b+1 are in flight while
     // batch b is composited (a dependent load would otherwise stall the in-order warp at its first use)
     uint32_t id_nxt = 0;
     Staged nxt;
-    if (lane < total) gather(point_list, means2D, conic_opacity, rgbd, range.x + lane, nxt);
+    if (lane < total) gather_id(__ldg(point_list + range.x + lane), G, nxt);
     if (32 + lane < total) id_nxt = __ldg(point_list + range.x + 32 + lane);
+    nxt_item = claim_item(ticket, num_items, order, ranges, lane);  // consumed after this item
     for (int b0 = 0; b0 < total; b0 += 32) {
-      if (__all_sync(0xffffffffu, !live)) break;
-      n_batches++;
-      __syncwarp();
-      if (b0 + lane < total) commit(nxt, g0s, g1s, cs, lane);
-      __syncwarp();
-      if (b0 + 32 + lane < total) gather_id(id_nxt, means2D, conic_opacity, rgbd, nxt);
-      if (b0 + 64 + lane < total) id_nxt = __ldg(point_list + range.x + b0 + 64 + lane);
+      if (__all_sync(FULL, !live)) break;
       const int nb = min(32, total - b0);
-      // phase 1: lane j tests staged Gaussian j against this warp's footprint
-      const bool may = lane < nb && footprint_may_hit(g0s[lane], g1s[lane], fx0, fx0 + (float)(ITEM_W - 1), fy0,
+      // phase 1: lane j tests staged Gaussian j (still in its registers) against this warp's footprint
+      const bool may = lane < nb && footprint_may_hit(nxt, fx0, fx0 + (float)(ITEM_W - 1), fy0,
                                                         fy0 + (float)(ITEM_H - 1));
-      uint32_t todo = __ballot_sync(0xffffffffu, may);
-      n_surv += __popc(todo);
+      uint32_t todo = __ballot_sync(FULL, may);
+      __syncwarp();
+      if (may) commit(nxt, g0s, g1s, cs, lane);
+      __syncwarp();
+      if (b0 + 32 + lane < total) gather_id(id_nxt, G, nxt);
+      if (b0 + 64 + lane < total) id_nxt = __ldg(point_list + range.x + b0 + 64 + lane);
       // phase 2: front-to-back over the survivors
       while (todo) {
         const int j = __ffs(todo) - 1;
@@ -235,7 +263,6 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
         const float cdy2 = __fmul_rn(__fmul_rn(g1.x, dy), dy);
         const float pw = pair_power(g0.z, __fsub_rn(g0.x, pxf), bdy, cdy2);
         if (!(pw >= g1.z) || pw > 0.0f) continue;
-        n_hit++;
         const float alpha = fminf(0.99f, __fmul_rn(g1.y, skgs_exp(pw)));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
@@ -254,15 +281,6 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
         last = (uint32_t)(b0 + j + 1);
       }
     }
-    if (stats) {
-      const unsigned long long dt = clock64() - t_start;
-      const uint32_t any_hit = __reduce_add_sync(0xffffffffu, n_hit);
-      if (lane == 0) {
-        unsigned long long* o = stats + (size_t)item * 6;
-        o[0] = (unsigned long long)tile; o[1] = (unsigned long long)total; o[2] = n_batches; o[3] = n_surv;
-        o[4] = any_hit; o[5] = dt;
-      }
-    }
     if (inside) {
       const size_t pid = (size_t)py * W + px;
       out_color[pid] = __fmaf_rn(T, bg0, C0);
@@ -279,12 +297,17 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // backward.  Same work items as the forward.
 // ------------------------------------------------------------------------------------------------------------------
-// Sum the parked rows (two per lane), leave each row total in the row's pad word, then lane s < n flushes slot s with
-// three 16-byte vector REDs: one RED set per (item, Gaussian).
-__device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id, int n, int lane, float ddelx_dx,
-                                            float ddely_dy, float* __restrict__ ggrad) {
+constexpr int RSLOTS = SKGS_RSLOTS, RSTRIDE = 33;  // reduction staging: rows of 32 + 1 pad word (conflict free)
+
+// Sum the parked rows (two per lane), leave each row total in the row's pad word, then lane s < n turns slot s into
+// gradients and flushes it with three 16-byte vector REDs: one RED set per (item, Gaussian).
+// Row order of a slot: S1x S1y Sxx Sxy Syy op r g b [z] with S.. the moments of q = o G dL/dalpha over the pixels:
+//   dL/dmean2D = -(A S1x + B S1y, C S1y + B S1x) * (W/2, H/2),   dL/dconic = -1/2 (Sxx, Sxy, Syy)   (App. A.7)
+template <int RV>
+__device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id, const float4* slot_abc, int n,
+                                            int lane, float ddelx_dx, float ddely_dy, float* __restrict__ ggrad) {
   __syncwarp();
-  for (int r = lane; r < n * RVALS; r += 32) {
+  for (int r = lane; r < n * RV; r += 32) {
     const float* row = part + r * RSTRIDE;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -295,60 +318,68 @@ __device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id
   }
   __syncwarp();
   if (lane < n) {
-    const float* t = part + lane * (RVALS * RSTRIDE) + 32;
-    const float mx = t[0 * RSTRIDE], my = t[1 * RSTRIDE], ca = t[2 * RSTRIDE], cb = t[3 * RSTRIDE];
-    const float cc = t[4 * RSTRIDE], op = t[5 * RSTRIDE], z = t[6 * RSTRIDE];
-    const float r = t[7 * RSTRIDE], g = t[8 * RSTRIDE], b = t[9 * RSTRIDE];
+    const float* t = part + lane * (RV * RSTRIDE) + 32;
+    const float S1x = t[0 * RSTRIDE], S1y = t[1 * RSTRIDE], Sxx = t[2 * RSTRIDE], Sxy = t[3 * RSTRIDE];
+    const float Syy = t[4 * RSTRIDE], op = t[5 * RSTRIDE];
+    const float r = t[6 * RSTRIDE], g = t[7 * RSTRIDE], b = t[8 * RSTRIDE];
+    const float z = RV > 9 ? t[9 * RSTRIDE] : 0.f;
+    const float4 abc = slot_abc[lane];  // conic A, B, C of the slot's Gaussian
     float* dst = ggrad + (size_t)slot_id[lane] * NGRAD;
-    red_add_v4(dst, mx * ddelx_dx, my * ddely_dy, -0.5f * ca, -0.5f * cb);
-    red_add_v4(dst + 4, -0.5f * cc, op, z, 0.f);
+    red_add_v4(dst, -(abc.x * S1x + abc.y * S1y) * ddelx_dx, -(abc.z * S1y + abc.y * S1x) * ddely_dy, -0.5f * Sxx,
+               -0.5f * Sxy);
+    red_add_v4(dst + 4, -0.5f * Syy, op, z, 0.f);
     red_add_v4(dst + 8, r, g, b, 0.f);
   }
   __syncwarp();
 }
 
+// AUX: a depth and/or alpha cotangent is present (upstream boundary B1 hands them over; the SK_GS training step does
+// not, and then the depth channel - two accumulators, one reduced value - is not carried at all)
+template <bool AUX>
 __global__ void __launch_bounds__(CW_THREADS, SKGS_BWD_MINBLOCKS)
 composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
                      uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
-                     const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
-                     const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
-                     const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
-                     const float* __restrict__ final_T, const float* __restrict__ dL_dpix,
-                     const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_map,
-                     float* __restrict__ ggrad) {
+                     const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                     const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
+                     const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
+                     const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth,
+                     const float* __restrict__ dL_dalpha_map, float* __restrict__ ggrad) {
+  constexpr int RV = AUX ? 10 : 9;
   __shared__ float4 s_g0[CW_WARPS][32];
   __shared__ float4 s_g1[CW_WARPS][32];
   __shared__ float4 s_c[CW_WARPS][32];
-  // cross-lane reduction through shared memory: every lane parks its 10 partial sums of up to RSLOTS surviving
-  // Gaussians (rows of 32 + 1 pad word, conflict free), then the 10*RSLOTS rows are summed two per lane - about 35
+  // cross-lane reduction through shared memory: every lane parks its RV partial sums of up to RSLOTS surviving
+  // Gaussians (rows of 32 + 1 pad word, conflict free), then the RV*RSLOTS rows are summed two per lane - about 35
   // instructions per surviving Gaussian instead of 100 for ten 5-step shuffle reductions
-  __shared__ float s_part[CW_WARPS][RSLOTS * RVALS * RSTRIDE];
+  __shared__ float s_part[CW_WARPS][RSLOTS * RV * RSTRIDE];
   __shared__ uint32_t s_slot_id[CW_WARPS][RSLOTS];
+  __shared__ float4 s_slot_abc[CW_WARPS][RSLOTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* g0s = s_g0[warp];
   float4* g1s = s_g1[warp];
   float4* cs = s_c[warp];
   float* part = s_part[warp];
   uint32_t* slot_id = s_slot_id[warp];
+  float4* slot_abc = s_slot_abc[warp];
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t* __restrict__ point_list = hdr->final_buf ? vals_b : vals_a;
   const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
   const size_t HW = (size_t)H * W;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const uint32_t num_items = (uint32_t)tiles * ITEMS_PER_TILE;
 
-  while (true) {
-    uint32_t item = 0;
-    if (lane == 0) item = atomicAdd(ticket, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= num_items) break;
-    const int tile = (int)order[item / ITEMS_PER_TILE];
-    const int sub = (int)(item % ITEMS_PER_TILE);
-    const int tx = tile % gx, ty = tile / gx;
+  Item nxt_item = claim_item(ticket, num_items, order, ranges, lane);
+  while (nxt_item.id < num_items) {
+    const Item it = nxt_item;
+    const int sub = (int)(it.id % ITEMS_PER_TILE);
+    const int tx = it.tile % gx, ty = it.tile / gx;
     const int X0 = tx * TILE + (sub & 1) * ITEM_W, Y0 = ty * TILE + (sub >> 1) * ITEM_H;
     const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const float fx0 = (float)X0, fy0 = (float)Y0;
-    const uint2 range = ranges[tile];
+    const uint2 range = it.range;
     const size_t pid = (size_t)py * W + px;
 
     const uint32_t last = inside ? n_contrib[pid] : 0u;
@@ -357,29 +388,30 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
     const float dp0 = inside ? dL_dpix[pid] : 0.f;
     const float dp1 = inside ? dL_dpix[HW + pid] : 0.f;
     const float dp2 = inside ? dL_dpix[2 * HW + pid] : 0.f;
-    const float dD = (inside && dL_ddepth) ? dL_ddepth[pid] : 0.f;
-    const float dA = (inside && dL_dalpha_map) ? dL_dalpha_map[pid] : 0.f;
+    const float dD = (AUX && inside && dL_ddepth) ? dL_ddepth[pid] : 0.f;
+    const float dA = (AUX && inside && dL_dalpha_map) ? dL_dalpha_map[pid] : 0.f;
     const float tail = bg0 * dp0 + bg1 * dp1 + bg2 * dp2 - dA;
     float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, acd = 0.f, la = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
     uint32_t mymax = last;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+    for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(FULL, mymax, o));
     // positions >= mymax contribute to no pixel of this item: start there and walk to the front
     int nslots = 0;
     uint32_t id_nxt = 0;
     Staged nxt;
-    if ((int)mymax - 1 - lane >= 0) gather(point_list, means2D, conic_opacity, rgbd, range.x + mymax - 1 - lane, nxt);
+    if ((int)mymax - 1 - lane >= 0) gather_id(__ldg(point_list + range.x + mymax - 1 - lane), G, nxt);
     if ((int)mymax - 33 - lane >= 0) id_nxt = __ldg(point_list + range.x + mymax - 33 - lane);
+    nxt_item = claim_item(ticket, num_items, order, ranges, lane);  // consumed after this item
     for (int top = (int)mymax; top > 0; top -= 32) {
-      __syncwarp();
-      if (top - 1 - lane >= 0) commit(nxt, g0s, g1s, cs, lane);
-      __syncwarp();
-      if (top - 33 - lane >= 0) gather_id(id_nxt, means2D, conic_opacity, rgbd, nxt);
-      if (top - 65 - lane >= 0) id_nxt = __ldg(point_list + range.x + top - 65 - lane);
       const int nb = min(32, top);
-      const bool may = lane < nb && footprint_may_hit(g0s[lane], g1s[lane], fx0, fx0 + (float)(ITEM_W - 1), fy0,
+      const bool may = lane < nb && footprint_may_hit(nxt, fx0, fx0 + (float)(ITEM_W - 1), fy0,
                                                         fy0 + (float)(ITEM_H - 1));
-      uint32_t todo = __ballot_sync(0xffffffffu, may);
+      uint32_t todo = __ballot_sync(FULL, may);
+      __syncwarp();
+      if (may) commit(nxt, g0s, g1s, cs, lane);
+      __syncwarp();
+      if (top - 33 - lane >= 0) gather_id(id_nxt, G, nxt);
+      if (top - 65 - lane >= 0) id_nxt = __ldg(point_list + range.x + top - 65 - lane);
       while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -390,58 +422,63 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
         const float bdy = __fmul_rn(g0.w, dy);
         const float cdy2 = __fmul_rn(__fmul_rn(g1.x, dy), dy);
         const float pw = pair_power(g0.z, dx, bdy, cdy2);
-        float G = 0.f, alpha = 0.f;
+        float G_ = 0.f, alpha = 0.f;
         bool valid = (pw >= g1.z) && (posn < last) && !(pw > 0.0f);
         if (valid) {
-          G = skgs_exp(pw);
-          alpha = fminf(0.99f, __fmul_rn(g1.y, G));
+          G_ = skgs_exp(pw);
+          alpha = fminf(0.99f, __fmul_rn(g1.y, G_));
           valid = !(alpha < 1.0f / 255.0f);
         }
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float a_mx = 0.f, a_my = 0.f, a_ca = 0.f, a_cb = 0.f, a_cc = 0.f, a_op = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f,
+        if (!__any_sync(FULL, valid)) continue;
+        float a_1x = 0.f, a_1y = 0.f, a_xx = 0.f, a_xy = 0.f, a_yy = 0.f, a_op = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f,
               a_z = 0.f;
         if (valid) {
           const float4 c = cs[j];
-          const float A = -2.0f * g0.z, B = -g0.w, Cc = -2.0f * g1.x, o = g1.y;
           const float inv = __fdividef(1.0f, 1.0f - alpha);
           T = T * inv;
           const float w = alpha * T;
           ac0 = fmaf(la, lc0 - ac0, ac0);
           ac1 = fmaf(la, lc1 - ac1, ac1);
           ac2 = fmaf(la, lc2 - ac2, ac2);
-          acd = fmaf(la, ld - acd, acd);
-          lc0 = c.x; lc1 = c.y; lc2 = c.z; ld = c.w;
-          float dL_dalpha = (c.x - ac0) * dp0 + (c.y - ac1) * dp1 + (c.z - ac2) * dp2 + (c.w - acd) * dD;
-          a_r = w * dp0; a_g = w * dp1; a_b = w * dp2; a_z = w * dD;
+          lc0 = c.x; lc1 = c.y; lc2 = c.z;
+          float dL_dalpha = (c.x - ac0) * dp0 + (c.y - ac1) * dp1 + (c.z - ac2) * dp2;
+          a_r = w * dp0; a_g = w * dp1; a_b = w * dp2;
+          if (AUX) {
+            acd = fmaf(la, ld - acd, acd);
+            ld = c.w;
+            dL_dalpha = fmaf(c.w - acd, dD, dL_dalpha);
+            a_z = w * dD;
+          }
           dL_dalpha *= T;
           la = alpha;
           dL_dalpha = fmaf(-Tfin * inv, tail, dL_dalpha);
-          const float dL_dG = o * dL_dalpha;
-          const float gdx = G * dx, gdy = G * dy;
-          a_mx = dL_dG * (-gdx * A - gdy * B);
-          a_my = dL_dG * (-gdy * Cc - gdx * B);
-          a_ca = gdx * dx * dL_dG;
-          a_cb = gdx * dy * dL_dG;
-          a_cc = gdy * dy * dL_dG;
-          a_op = G * dL_dalpha;
+          a_op = G_ * dL_dalpha;
+          const float q = g1.y * a_op;  // o G dL/dalpha
+          const float qx = q * dx, qy = q * dy;
+          a_1x = qx; a_1y = qy;
+          a_xx = qx * dx; a_xy = qx * dy; a_yy = qy * dy;
         }
         // park the partial sums of this Gaussian in slot `nslots`
         {
-          float* row = part + nslots * (RVALS * RSTRIDE) + lane;
-          row[0 * RSTRIDE] = a_mx; row[1 * RSTRIDE] = a_my; row[2 * RSTRIDE] = a_ca; row[3 * RSTRIDE] = a_cb;
-          row[4 * RSTRIDE] = a_cc; row[5 * RSTRIDE] = a_op; row[6 * RSTRIDE] = a_z; row[7 * RSTRIDE] = a_r;
-          row[8 * RSTRIDE] = a_g; row[9 * RSTRIDE] = a_b;
-          if (lane == 0) slot_id[nslots] = __float_as_uint(g1.w);
+          float* row = part + nslots * (RV * RSTRIDE) + lane;
+          row[0 * RSTRIDE] = a_1x; row[1 * RSTRIDE] = a_1y; row[2 * RSTRIDE] = a_xx; row[3 * RSTRIDE] = a_xy;
+          row[4 * RSTRIDE] = a_yy; row[5 * RSTRIDE] = a_op; row[6 * RSTRIDE] = a_r; row[7 * RSTRIDE] = a_g;
+          row[8 * RSTRIDE] = a_b;
+          if (AUX) row[9 * RSTRIDE] = a_z;
+          if (lane == 0) {
+            slot_id[nslots] = __float_as_uint(g1.w);
+            slot_abc[nslots] = make_float4(-2.0f * g0.z, -g0.w, -2.0f * g1.x, 0.f);
+          }
         }
         nslots++;
         if (nslots == RSLOTS) {
-          flush_slots(part, slot_id, nslots, lane, ddelx_dx, ddely_dy, ggrad);
+          flush_slots<RV>(part, slot_id, slot_abc, nslots, lane, ddelx_dx, ddely_dy, ggrad);
           nslots = 0;
         }
       }
     }
     if (nslots > 0) {
-      flush_slots(part, slot_id, nslots, lane, ddelx_dx, ddely_dy, ggrad);
+      flush_slots<RV>(part, slot_id, slot_abc, nslots, lane, ddelx_dx, ddely_dy, ggrad);
       nslots = 0;
     }
   }
@@ -450,8 +487,6 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------
-unsigned long long* g_item_stats = nullptr;  // debug: per-item counters (skgs_debug_set_item_stats)
-
 static int persistent_grid(const void* kernel) {
   int dev = 0, sms = 0, occ = 0;
   cudaGetDevice(&dev);
@@ -462,14 +497,23 @@ static int persistent_grid(const void* kernel) {
   return sms * occ;
 }
 
+static GeomIn geom_in(const char* geom, const skgs_raster_layout& lay) {
+  GeomIn G;
+  G.means2D = reinterpret_cast<const float2*>(geom + lay.means2D);
+  G.conic_opacity = reinterpret_cast<const float4*>(geom + lay.conic_opacity);
+  G.rgbd = reinterpret_cast<const float4*>(geom + lay.rgbd);
+  G.cull = reinterpret_cast<const float4*>(geom + lay.cull);
+  return G;
+}
+
 int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st) {
   const int tiles = rp.gx * rp.gy;
   if (tiles == 0) return SKGS_OK;
   {
     ProfScope prof_("tile_order_kernel", st);
-    tile_order_kernel<<<1, TO_THREADS, 0, st>>>(reinterpret_cast<const uint2*>(img + lay.ranges), tiles,
-                                                reinterpret_cast<uint32_t*>(img + lay.tile_order),
-                                                reinterpret_cast<uint32_t*>(img + lay.work_counters));
+    SKGS_CUDA(launch_pdl(tile_order_kernel, dim3(1), dim3(TO_THREADS), 0, st, reinterpret_cast<uint2*>(img + lay.ranges),
+                         tiles, reinterpret_cast<uint32_t*>(img + lay.tile_order),
+                         reinterpret_cast<uint32_t*>(img + lay.work_counters)));
     SKGS_CHECK_LAUNCH("tile_order_kernel");
   }
   return SKGS_OK;
@@ -485,47 +529,49 @@ int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char
   const int grid = want < grid_cap ? want : grid_cap;
   {
     ProfScope prof_("composite_fwd_kernel", st);
-    composite_fwd_kernel<<<grid, CW_THREADS, 0, st>>>(
-        rp.W, rp.H, rp.gx, tiles, reinterpret_cast<const uint32_t*>(img + lay.tile_order),
-        reinterpret_cast<uint32_t*>(img + lay.work_counters), reinterpret_cast<const uint2*>(img + lay.ranges),
-        reinterpret_cast<const uint32_t*>(binning + lay.point_list),
-        reinterpret_cast<const float2*>(geom + lay.means2D), reinterpret_cast<const float4*>(geom + lay.conic_opacity),
-        reinterpret_cast<const float4*>(geom + lay.rgbd), rp.bg, out_color, out_depth, out_alpha,
-        reinterpret_cast<uint32_t*>(img + lay.n_contrib), reinterpret_cast<float*>(img + lay.final_T),
-        g_item_stats);
+    SKGS_CUDA(launch_pdl(composite_fwd_kernel, dim3(grid), dim3(CW_THREADS), 0, st, rp.W, rp.H, rp.gx, tiles,
+                         reinterpret_cast<const uint32_t*>(img + lay.tile_order),
+                         reinterpret_cast<uint32_t*>(img + lay.work_counters),
+                         reinterpret_cast<const uint2*>(img + lay.ranges),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
+                         reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
+                         out_color, out_depth, out_alpha, reinterpret_cast<uint32_t*>(img + lay.n_contrib),
+                         reinterpret_cast<float*>(img + lay.final_T)));
     SKGS_CHECK_LAUNCH("composite_fwd_kernel");
   }
   return SKGS_OK;
 }
 
+// The per-Gaussian accumulators (geom_grads) are zero on entry: the forward zeroes them, preprocess_bwd re-zeroes them
+// (and the backward ticket) after consuming them - no memset between the loss and this kernel.
 int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning, const char* img,
                          const skgs_raster_layout& lay, const float* dL_dcolor, const float* dL_ddepth,
                          const float* dL_dalpha, cudaStream_t st) {
   float* ggrad = reinterpret_cast<float*>(geom + lay.geom_grads);
-  SKGS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)rp.P * NGRAD * sizeof(float), st));
   const int tiles = rp.gx * rp.gy;
   if (tiles == 0 || rp.P == 0) return SKGS_OK;
   uint32_t* counters = reinterpret_cast<uint32_t*>(const_cast<char*>(img) + lay.work_counters);
-  SKGS_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(uint32_t), st));  // backward may be re-run on the same state
-  static int grid_cap = 0;
-  if (grid_cap == 0) grid_cap = persistent_grid((const void*)composite_bwd_kernel);
+  const bool aux = dL_ddepth != nullptr || dL_dalpha != nullptr;
+  static int grid_cap[2] = {0, 0};
+  if (grid_cap[aux] == 0)
+    grid_cap[aux] = persistent_grid(aux ? (const void*)composite_bwd_kernel<true> : (const void*)composite_bwd_kernel<false>);
   const int want = (tiles * ITEMS_PER_TILE + CW_WARPS - 1) / CW_WARPS;
-  const int grid = want < grid_cap ? want : grid_cap;
+  const int grid = want < grid_cap[aux] ? want : grid_cap[aux];
   {
     ProfScope prof_("composite_bwd_kernel", st);
-    composite_bwd_kernel<<<grid, CW_THREADS, 0, st>>>(
-        rp.W, rp.H, rp.gx, tiles, reinterpret_cast<const uint32_t*>(img + lay.tile_order), counters + 1,
-        reinterpret_cast<const uint2*>(img + lay.ranges), reinterpret_cast<const uint32_t*>(binning + lay.point_list),
-        reinterpret_cast<const float2*>(geom + lay.means2D), reinterpret_cast<const float4*>(geom + lay.conic_opacity),
-        reinterpret_cast<const float4*>(geom + lay.rgbd), rp.bg, reinterpret_cast<const uint32_t*>(img + lay.n_contrib),
-        reinterpret_cast<const float*>(img + lay.final_T), dL_dcolor, dL_ddepth, dL_dalpha, ggrad);
+    auto kern = aux ? composite_bwd_kernel<true> : composite_bwd_kernel<false>;
+    SKGS_CUDA(launch_pdl(kern, dim3(grid), dim3(CW_THREADS), 0, st, rp.W, rp.H, rp.gx, tiles,
+                         reinterpret_cast<const uint32_t*>(img + lay.tile_order), counters + 1,
+                         reinterpret_cast<const uint2*>(img + lay.ranges),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
+                         reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
+                         reinterpret_cast<const uint32_t*>(img + lay.n_contrib),
+                         reinterpret_cast<const float*>(img + lay.final_T), dL_dcolor, dL_ddepth, dL_dalpha, ggrad));
     SKGS_CHECK_LAUNCH("composite_bwd_kernel");
   }
   return SKGS_OK;
 }
 
 }  // namespace skgs
-
-extern "C" __attribute__((visibility("default"))) void skgs_debug_set_item_stats(void* p) {
-  skgs::g_item_stats = reinterpret_cast<unsigned long long*>(p);
-}

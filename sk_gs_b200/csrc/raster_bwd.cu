@@ -27,17 +27,22 @@ __global__ void __launch_bounds__(PB_THREADS)
 preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ cov3D_in, const int32_t* __restrict__ radii,
-                      const uint8_t* __restrict__ clamped, const float* __restrict__ ggrad,
-                      float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
+                      const uint8_t* __restrict__ clamped, float* __restrict__ ggrad,
+                      uint32_t* __restrict__ bwd_ticket, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales,
                       float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D) {
   __shared__ float s_V[16], s_P[16], s_cam[3];
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (tid < 16) {
     s_V[tid] = rp.view[tid];
     s_P[tid] = rp.proj[tid];
   }
   if (tid < 3) s_cam[tid] = rp.campos[tid];
+  // restore the invariants composite_bwd relies on, so that a second backward on the same state needs no memset:
+  // its work ticket is 0 and the per-Gaussian accumulators are zero outside the composite_bwd -> here window
+  if (blockIdx.x == 0 && tid == 0) *bwd_ticket = 0u;
   __syncthreads();
   const int i = blockIdx.x * PB_THREADS + tid;
   if (i >= rp.P) return;
@@ -47,8 +52,9 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   const bool vis = radii[i] > 0;
   float g[NGRAD];
   {
-    const float4* gp = reinterpret_cast<const float4*>(ggrad + (size_t)i * NGRAD);
+    float4* gp = reinterpret_cast<float4*>(ggrad + (size_t)i * NGRAD);
     const float4 a = gp[0], b = gp[1], c = gp[2];
+    gp[0] = gp[1] = gp[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
     g[8] = c.x; g[9] = c.y; g[10] = c.z; g[11] = c.w;
   }
@@ -307,19 +313,20 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
 
 int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
-                          const int32_t* radii, char* geom, const skgs_raster_layout& lay, float* dL_dmeans3D,
-                          float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity, float* dL_dscales,
-                          float* dL_drotations, float* dL_dcov3D, cudaStream_t st) {
+                          const int32_t* radii, char* geom, const skgs_raster_layout& lay, uint32_t* bwd_ticket,
+                          float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
+                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, cudaStream_t st) {
   if (rp.P == 0) return SKGS_OK;
   (void)colors_precomp;
   const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom + lay.cov3D);
   {
     ProfScope prof_("preprocess_bwd_kernel", st);
-    preprocess_bwd_kernel<<<(rp.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, st>>>(
-      rp, means3D, shs, cov3D_precomp ? nullptr : scales, rotations, cov, radii,
-      reinterpret_cast<const uint8_t*>(geom + lay.clamped), reinterpret_cast<const float*>(geom + lay.geom_grads),
-      dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
-  SKGS_CHECK_LAUNCH("preprocess_bwd_kernel");
+    SKGS_CUDA(launch_pdl(preprocess_bwd_kernel, dim3((rp.P + PB_THREADS - 1) / PB_THREADS), dim3(PB_THREADS), 0, st, rp,
+                         means3D, shs, cov3D_precomp ? nullptr : scales, rotations, cov, radii,
+                         reinterpret_cast<const uint8_t*>(geom + lay.clamped),
+                         reinterpret_cast<float*>(geom + lay.geom_grads), bwd_ticket, dL_dmeans3D, dL_dmeans2D, dL_dsh,
+                         dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D));
+    SKGS_CHECK_LAUNCH("preprocess_bwd_kernel");
   }
   return SKGS_OK;
 }

@@ -48,7 +48,6 @@ class _Capacity:
     def __init__(self):
         self.last = {}
         self.growth = 1.25
-        self.fixed: Optional[int] = None  # set_fixed_capacity(): never look at R on the host (CUDA-graph friendly)
 
     def get(self, key):
         return self.last.get(key)
@@ -61,15 +60,16 @@ _capacity = _Capacity()
 _pinned = {}
 
 
-def set_fixed_capacity(R_cap: Optional[int]):
-    """R_cap entries for every call and no host wait at all (CUDA-graph capturable).  If R exceeds R_cap the image of that
-    call is INVALID: header.overflow = 1, also copied asynchronously into `last_header_words(device)[3]`."""
-    _capacity.fixed = None if R_cap is None else int(R_cap)
+def new_header_words() -> Tensor:
+    """A pinned host int32[4] that a fixed-capacity forward (`rasterize_forward(..., fixed_capacity=, header_words=)`)
+    fills asynchronously with {R, num_visible, -, overflow}.  Every captured CUDA graph owns one, so that the overflow
+    flag of one graph is never confused with another's (allocate it BEFORE stream capture starts)."""
+    return torch.zeros(4, dtype=torch.int32).pin_memory()
 
 
 def last_header_words(device) -> Tensor:
-    """Pinned host int32[4] = {R, num_visible, -, overflow} of the most recent forward on the current stream (valid after
-    that forward has completed on the device)."""
+    """Pinned host int32[4] = {R, num_visible, -, overflow} of the most recent EAGER forward on `device` (valid after
+    that forward has completed on the device).  Fixed-capacity (graph) calls write to their own buffer instead."""
     return _pinned_words(torch.device(device))
 
 
@@ -110,6 +110,27 @@ class RasterState(NamedTuple):
     layout: object
     num_rendered: int
 
+    def header(self) -> '_lib.RasterHeader':
+        """Host copy of the device header (synchronises the device)."""
+        raw = bytes(self.geom[int(self.layout.header):int(self.layout.header) + C.sizeof(_lib.RasterHeader)].cpu().numpy())
+        return _lib.RasterHeader.from_buffer_copy(raw)
+
+    def sorted_lists(self):
+        """(keys uint64-as-int64 [R], point_list int32 [R]) sorted by (tile, depth): the binning buffer the last executed
+        radix pass wrote (header.final_buf; synchronises the device).  R = min(num_rendered, R_cap)."""
+        h = self.header()
+        lay = self.layout
+        R = min(int(h.num_rendered), int(self.R_cap))
+        ko, vo = (lay.keys_b, lay.vals_b) if h.final_buf else (lay.keys_a, lay.vals_a)
+        keys = self.binning[ko:ko + 8 * R].view(torch.int64)
+        vals = self.binning[vo:vo + 4 * R].view(torch.int32)
+        return keys, vals
+
+    @property
+    def overflow_ptr(self) -> int:
+        """Device address of header.overflow (uint32) of this call: non-zero <=> R exceeded the binning capacity."""
+        return self.geom.data_ptr() + int(self.layout.header) + 12
+
 
 def _make_settings(rs: GaussianRasterizationSettings, device, quat_wxyz: bool, debug_flags: int = 0):
     view, proj, campos = _f32c(rs.viewmatrix.to(device)), _f32c(rs.projmatrix.to(device)), _f32c(rs.campos.to(device))
@@ -128,8 +149,15 @@ def layout_query(P: int, W: int, H: int, R_cap: int):
 
 
 def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs=None, colors_precomp=None,
-                      scales=None, rotations=None, cov3D_precomp=None, quat_wxyz: bool = True, debug_flags: int = 0):
-    """Non-autograd forward.  Returns (color, depth, alpha, radii, RasterState)."""
+                      scales=None, rotations=None, cov3D_precomp=None, quat_wxyz: bool = True, debug_flags: int = 0,
+                      fixed_capacity: Optional[int] = None, header_words: Optional[Tensor] = None):
+    """Non-autograd forward.  Returns (color, depth, alpha, radii, RasterState).
+
+    `fixed_capacity`: size the binning arena for exactly that many (Gaussian, tile) pairs and never look at R on the host
+    (no wait at all: CUDA-graph capturable).  It is a property of THIS call - nothing process-wide changes.  If R exceeds
+    it the image of the call is INVALID: `header.overflow` = 1 on the device (RasterState.overflow_ptr, which
+    skgs_adam_step can be told to honour) and in `header_words[3]` once the call has completed.  The caller owns the
+    check: see HotPath.overflowed() / TrainLoop.replay()."""
     L = _lib.lib()
     if not means3D.is_cuda:
         raise RuntimeError('means3D must be a CUDA tensor (sk_gs_b200 has no CPU path)')
@@ -157,43 +185,55 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
         color = torch.empty(3, H, W, dtype=torch.float32, device=device)
         depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
         alpha = torch.empty(1, H, W, dtype=torch.float32, device=device)
-        fixed = _capacity.fixed
-        words = _pinned_words(device)  # {R, num_visible, -, overflow}; in fixed mode it is written but never waited on
-        _lib.check(L.skgs_raster_forward_geometry(
-            C.byref(s), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(opacities),
-            _lib.ptr(scales), _lib.ptr(rotations), _lib.ptr(cov3D_precomp), geom.data_ptr(), radii.data_ptr(),
-            words.data_ptr(), st), 'skgs_raster_forward_geometry')
+        fixed = None if fixed_capacity is None else int(fixed_capacity)
+        if fixed is not None and header_words is None:
+            raise RuntimeError('fixed_capacity needs header_words=new_header_words(): somebody has to own the overflow flag')
+        # {R, num_visible, -, overflow}; in fixed mode it is written but never waited on
+        words = header_words if fixed is not None else _pinned_words(device)
         key = (device.index, P, W, H)
+        est = _capacity.get(key)
         R_known = None
-        if fixed is not None:
-            R_cap = fixed
-        else:
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            est = _capacity.get(key)
-            if est is None:  # first call for this shape: one blocking read of R, like the reference does every call
-                ev.synchronize()
-                R_known = int(words[0].item()) & 0xffffffff
-                est = R_known
-            R_cap = max(int(est * _capacity.growth) + 4096, 4096)
-        while True:
-            lay = layout_query(P, W, H, R_cap)
-            binning = torch.empty(lay.binning_bytes, dtype=torch.uint8, device=device)
-            hint = R_known if R_known is not None else (_capacity.get(key) or R_cap)
+
+        def geometry(binning, R_cap):
+            _lib.check(L.skgs_raster_forward_geometry(
+                C.byref(s), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(opacities),
+                _lib.ptr(scales), _lib.ptr(rotations), _lib.ptr(cov3D_precomp), geom.data_ptr(), radii.data_ptr(),
+                _lib.ptr(binning), R_cap, img.data_ptr(), words.data_ptr(), st), 'skgs_raster_forward_geometry')
+
+        def render(binning, R_cap, hint, keys_emitted):
             _lib.check(L.skgs_raster_forward_render(
                 C.byref(s), P, geom.data_ptr(), binning.data_ptr(), R_cap, int(hint), img.data_ptr(), radii.data_ptr(),
-                color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), words.data_ptr() if fixed is not None else None,
-                st), 'skgs_raster_forward_render')
+                int(keys_emitted), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                words.data_ptr() if fixed is not None else None, st), 'skgs_raster_forward_render')
+
+        if fixed is not None or est is not None:
+            # capacity known up front (a captured graph's fixed one, or the estimate from the previous call of this
+            # shape): preprocess, scan and key emission are ONE kernel
+            R_cap = fixed if fixed is not None else max(int(est * _capacity.growth) + 4096, 4096)
+            lay = layout_query(P, W, H, R_cap)
+            binning = torch.empty(lay.binning_bytes, dtype=torch.uint8, device=device)
+            geometry(binning, R_cap)
+            if fixed is None:
+                ev = torch.cuda.Event()
+                ev.record(stream)  # the header words are on their way; everything below is queued behind them
+            render(binning, R_cap, est if est is not None else R_cap, True)
             if fixed is not None:
                 R_known = -1
-                break
-            if R_known is None:
-                ev.synchronize()  # preprocess+scan finished long ago; everything after it is already queued
+            else:
+                ev.synchronize()  # preprocess finished long ago; the GPU is busy with the rest of the forward
                 R_known = int(words[0].item()) & 0xffffffff
+                _capacity.put(key, R_known)
+        else:  # first call for this shape: one blocking read of R, like the reference does on every call
+            geometry(None, 0)
+            stream.synchronize()
+            R_known = int(words[0].item()) & 0xffffffff
             _capacity.put(key, R_known)
-            if R_known <= R_cap:
-                break
-            R_cap = int(R_known * _capacity.growth) + 4096  # under-estimated: redo binning + compositing
+            R_cap = -1  # forces the sizing pass below
+        while fixed is None and R_known > R_cap:  # first call, or under-estimated: size the arena from R, emit + render
+            R_cap = max(int(R_known * _capacity.growth) + 4096, 4096)
+            lay = layout_query(P, W, H, R_cap)
+            binning = torch.empty(lay.binning_bytes, dtype=torch.uint8, device=device)
+            render(binning, R_cap, R_known, False)
     state = RasterState(s, keep + (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp), P, M,
                         R_cap, geom, binning, img, radii, lay, R_known)
     return color, depth, alpha, radii, state

@@ -34,7 +34,8 @@ class GradArena:
     preprocess-backward, so `allreduce(chunks=...)` can reduce them while the LBS / FK backward of the same step is
     still running on the compute stream - then the per-joint blocks, then the screen-space statistic."""
 
-    def __init__(self, shapes: Dict[str, Sequence[int]], device, order: Optional[Sequence[str]] = None):
+    def __init__(self, shapes: Dict[str, Sequence[int]], device, order: Optional[Sequence[str]] = None,
+                 allocate: bool = True):
         self.names = list(order) if order is not None else sorted(shapes, key=lambda n: -int(torch.Size(shapes[n]).numel()))
         self.shapes = {n: torch.Size(shapes[n]) for n in self.names}
         self.offsets: Dict[str, Tuple[int, int]] = {}
@@ -43,7 +44,8 @@ class GradArena:
             k = self.shapes[n].numel()
             self.offsets[n] = (o, o + k)
             o = (o + k + 3) // 4 * 4  # every block starts on a 16-byte boundary (vector all-reduce of sub-ranges)
-        self.flat = torch.zeros(o, dtype=torch.float32, device=device)
+        self.numel = o
+        self.flat = torch.zeros(o, dtype=torch.float32, device=device) if allocate else None
 
     def view(self, name: str) -> Tensor:
         a, b = self.offsets[name]
@@ -70,9 +72,10 @@ class GradArena:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return []
         n = self.flat.numel()
-        step = (n + chunks - 1) // max(chunks, 1)
+        chunks = max(int(chunks), 1)
+        step = max((n + chunks - 1) // chunks, 1)
         works = []
-        for a in range(0, n, max(step, 1)):
+        for a in range(0, n, step):
             w = dist.all_reduce(self.flat[a:a + step], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
             if async_op:
                 works.append(w)
@@ -91,21 +94,21 @@ class SymmGradArena(GradArena):
     available (`self.multimem` tells which one is active)."""
 
     def __init__(self, shapes, device, order=None, group=None):
-        super().__init__(shapes, device, order)
+        super().__init__(shapes, device, order, allocate=False)
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
-        n = (self.flat.numel() + 3) // 4 * 4
+        n = (self.numel + 3) // 4 * 4
         buf = symm_mem.empty(n, dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(buf, self.group.group_name)
         buf.zero_()
         self.flat_padded = buf
-        self.flat = buf[:self.flat.numel()]
+        self.flat = buf[:self.numel]
         self.multimem = bool(self.handle.multicast_ptr)
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
 
     def allreduce(self, scale: float = 1.0, group=None, chunks: int = 1, async_op: bool = False):
-        if not self.multimem:
-            return super().allreduce(scale, group, chunks, async_op)
+        if not self.multimem:  # NCCL path of the base class, on the group this arena was built for
+            return super().allreduce(scale, group if group is not None else self.group, chunks, async_op)
         if scale != 1.0:
             self.flat.mul_(scale)
         self.allreduce_range(0, self.flat_padded.numel())

@@ -34,14 +34,22 @@ def _as_chw(image: Tensor) -> Tensor:
     return _f32c(image)
 
 
-def _target(target: Tensor) -> Tuple[Tensor, int]:
+def _target(target: Tensor, layout: Optional[str] = None) -> Tuple[Tensor, int]:
     """(tensor, pixel stride): channel-major targets are used as they are (stride 0); pixel-major RGB / RGBA targets
-    (datasets hand out [H,W,3|4], sk_gs.py:1525 slices [..., :3]) are read in place with stride 3 / 4."""
+    (datasets hand out [H,W,3|4], sk_gs.py:1525 slices [..., :3]) are read in place with stride 3 / 4.
+    `layout` ('chw' | 'hwc') overrides the shape heuristic, which cannot tell [3,H,W] from [H,W,3|4] when H or W is 3
+    or 4 (it then prefers pixel-major, what the datasets hand out)."""
     if target.ndim == 4:
+        if target.shape[0] != 1:
+            raise RuntimeError('image loss takes one target per call, got a batch of %d' % target.shape[0])
         target = target[0]
     if target.ndim != 3:
         raise RuntimeError(f'expected a target with 3 or 4 dims, got shape {tuple(target.shape)}')
-    if target.shape[0] == 3 and target.shape[-1] not in (3, 4):
+    if layout not in (None, 'chw', 'hwc'):
+        raise ValueError(f"layout must be 'chw', 'hwc' or None, got {layout!r}")
+    if layout == 'chw' or (layout is None and target.shape[0] == 3 and target.shape[-1] not in (3, 4)):
+        if target.shape[0] != 3:
+            raise RuntimeError(f'channel-major target needs 3 channels, got shape {tuple(target.shape)}')
         return _f32c(target), 0
     if target.shape[-1] not in (3, 4):
         raise RuntimeError(f'cannot interpret target of shape {tuple(target.shape)}')
@@ -52,14 +60,15 @@ def _target(target: Tensor) -> Tuple[Tensor, int]:
 
 
 def image_loss_raw(image: Tensor, target: Tensor, w_image: float = 0.8, w_ssim: float = 0.2, method: str = 'l1',
-                   grad_scale: float = 1.0, need_grad: bool = True, out: Optional[dict] = None):
+                   grad_scale: float = 1.0, need_grad: bool = True, out: Optional[dict] = None,
+                   target_layout: Optional[str] = None):
     """Autograd-free call: returns (terms float32[3] on the device = pixel term, 1 - mean SSIM, weighted total;
     dL/dimage [3,H,W] or None).  `out` may carry preallocated 'terms', 'dL_dimage', 'workspace' (CUDA-graph capture)."""
     if not image.is_cuda or not target.is_cuda:
         raise RuntimeError('image loss needs CUDA tensors (sk_gs_b200 has no CPU path)')
     L = _lib.lib()
     img = _as_chw(image.detach())
-    tgt, stride = _target(target.detach())
+    tgt, stride = _target(target.detach(), target_layout)
     H, W = img.shape[1:]
     th, tw = (tgt.shape[1:] if stride == 0 else tgt.shape[:2])
     if (th, tw) != (H, W):

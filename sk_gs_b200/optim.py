@@ -19,12 +19,15 @@ from . import _lib
 def adam_step_raw(params: Sequence[Tensor], grads: Sequence[Tensor], exp_avgs: Sequence[Tensor],
                   exp_avg_sqs: Sequence[Tensor], lrs: Sequence[float], step: int, beta1: float = 0.9,
                   beta2: float = 0.999, eps: float = 1e-15, grad_scale: float = 1.0,
-                  knn_indices: Optional[Sequence[Optional[Tensor]]] = None, dynamic_hyper: Optional[Tensor] = None):
+                  knn_indices: Optional[Sequence[Optional[Tensor]]] = None, dynamic_hyper: Optional[Tensor] = None,
+                  skip_flag_ptr: Optional[int] = None):
     """In-place Adam update of `params` (autograd-free; CUDA-graph capturable: nothing is allocated).
     `knn_indices[i]` (int64 [rows, K]) marks tensor i as having a compact [rows, K] gradient (see include/skgs_b200.h).
     `lrs[i]` is a float, or `(lr, lr2, period, split)` for two interleaved param groups in one array (element e uses lr
     if e % period < split else lr2 - the merged SH array, see include/skgs_b200.h).
-    `dynamic_hyper` (device float32 [1 + 2n], see `adam_hyper`) overrides step / lr inside a replayed CUDA graph."""
+    `dynamic_hyper` (device float32 [1 + 2n], see `adam_hyper`) overrides step / lr inside a replayed CUDA graph.
+    `skip_flag_ptr`: device address of a uint32; non-zero at execution time turns the step into a no-op (pass
+    RasterState.overflow_ptr so that gradients of an overflowed fixed-capacity render never reach the parameters)."""
     n = len(params)
     if not (len(grads) == len(exp_avgs) == len(exp_avg_sqs) == len(lrs) == n):
         raise RuntimeError('adam_step_raw: argument lists differ in length')
@@ -63,7 +66,8 @@ def adam_step_raw(params: Sequence[Tensor], grads: Sequence[Tensor], exp_avgs: S
                 table[j] = _lib.AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
                                            float(lr), float(lr2), int(period), int(split), cols, K, _lib.ptr(idx))
             _lib.check(L.skgs_adam_step(table, hi - lo, int(step), float(beta1), float(beta2), float(eps),
-                                        float(grad_scale), _lib.ptr(dynamic_hyper), st), 'skgs_adam_step')
+                                        float(grad_scale), _lib.ptr(dynamic_hyper), skip_flag_ptr, st),
+                       'skgs_adam_step')
 
 
 def adam_hyper(lrs: Sequence[float], step: int, beta1: float = 0.9, beta2: float = 0.999) -> List[float]:
@@ -76,42 +80,30 @@ def adam_hyper(lrs: Sequence[float], step: int, beta1: float = 0.9, beta2: float
     return out
 
 
-class Adam:
-    """torch.optim.Adam look-alike (no weight decay, amsgrad or maximize - the reference uses none of them)."""
+class Adam(torch.optim.Optimizer):
+    """`torch.optim.Adam` with the update done by ONE launch of skgs_adam_step per step (no weight decay, amsgrad or
+    maximize - the reference uses none of them).
+
+    It IS a `torch.optim.Optimizer`: `param_groups`, `state` (per parameter 'step' tensor, 'exp_avg', 'exp_avg_sq' - the
+    keys and types torch.optim.Adam uses, so checkpoints are interchangeable with it), `state_dict()` /
+    `load_state_dict()`, `add_param_group()`, `zero_grad()`, lr schedulers and `GradScaler.step` all work, and so does the
+    reference's `GaussianSplatting.change_optimizer` (networks/gaussian_splatting.py:515-563), which tests
+    `isinstance(optimizers, torch.optim.Optimizer)` and edits `group['params'][0]` / `optimizer.state[...]` in place when
+    densification clones, splits or prunes Gaussians."""
 
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
-        groups = list(params)
-        if len(groups) == 0:
-            raise ValueError('optimizer got an empty parameter list')
-        if not isinstance(groups[0], dict):
-            groups = [{'params': groups}]
-        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps)
-        self.param_groups: List[dict] = []
-        self.state = {}
-        for g in groups:
-            self.add_param_group(g)
-
-    def add_param_group(self, group: dict):
-        group = dict(group)
-        ps = group['params']
-        group['params'] = [ps] if isinstance(ps, Tensor) else list(ps)
-        for k, v in self.defaults.items():
-            group.setdefault(k, v)
-        self.param_groups.append(group)
-
-    def zero_grad(self, set_to_none: bool = True):
-        for group in self.param_groups:
-            for p in group['params']:
-                if p.grad is not None:
-                    if set_to_none:
-                        p.grad = None
-                    else:
-                        p.grad.zero_()
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
+            raise ValueError(f'invalid Adam hyper-parameters lr={lr} betas={betas} eps={eps}')
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
 
     @torch.no_grad()
-    def step(self, knn_grads: Optional[dict] = None):
+    def step(self, closure=None, knn_grads: Optional[dict] = None):
         """One update of every parameter that has a gradient.  `knn_grads` optionally maps a parameter to
         `(grad [rows, K], indices int64 [rows, K])` - the compact gradient of the skinning table."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         knn_grads = knn_grads or {}
         buckets = {}
         for group in self.param_groups:
@@ -120,14 +112,16 @@ class Adam:
                 compact = knn_grads.get(p)
                 if p.grad is None and compact is None:
                     continue
-                st = self.state.get(p)
-                if st is None:
-                    st = self.state[p] = {'step': 0, 'exp_avg': torch.zeros_like(p, memory_format=torch.contiguous_format),
-                                          'exp_avg_sq': torch.zeros_like(p, memory_format=torch.contiguous_format)}
+                st = self.state[p]
+                if len(st) == 0:
+                    st['step'] = torch.tensor(0.0, dtype=torch.float32)  # host tensor, like torch's default (capturable=False)
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st['step'] += 1
                 g, idx = (p.grad.contiguous(), None) if compact is None else compact
-                buckets.setdefault(key + (st['step'],), []).append((p, g, st, float(group['lr']), idx))
+                buckets.setdefault(key + (int(st['step']),), []).append((p, g, st, float(group['lr']), idx))
         for (betas, eps, step), items in buckets.items():
             adam_step_raw([i[0].data for i in items], [i[1] for i in items], [i[2]['exp_avg'] for i in items],
                           [i[2]['exp_avg_sq'] for i in items], [i[3] for i in items], step, betas[0], betas[1], eps,
                           knn_indices=[i[4] for i in items])
+        return loss

@@ -106,7 +106,8 @@ class HotPath:
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def step_grads(self, view: int, dL_dimage: Optional[Tensor], compact_sp_W: bool = False, before_backward=None,
                    arena=None, after_forward=None, mid_backward=None, target: Optional[Tensor] = None,
-                   loss: Optional[dict] = None):
+                   loss: Optional[dict] = None, fixed_capacity: Optional[int] = None,
+                   header_words: Optional[Tensor] = None):
         """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
         nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
         (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
@@ -135,7 +136,9 @@ class HotPath:
                                                                             p['opacity'], d_xyz, d_rot, d_scale)
             sh = p['shs'] if 'shs' in p else torch.cat((p['f_dc'], p['f_rest']), dim=1)
             color, depth, alpha, radii, st = DGR.rasterize_forward(self.settings[view], points, opacity, shs=sh,
-                                                                   scales=scales, rotations=rotations, quat_wxyz=False)
+                                                                   scales=scales, rotations=rotations, quat_wxyz=False,
+                                                                   fixed_capacity=fixed_capacity,
+                                                                   header_words=header_words)
             join_after = after_forward(radii) if after_forward is not None else None  # e.g. radii MAX on a side stream
             if before_backward is not None:
                 before_backward()  # e.g. join the stream that uploads dL_dimage / the target while the forward runs
@@ -174,7 +177,7 @@ class HotPath:
         if join_mid is not None:
             join_mid()
         out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
-               'loss_terms': loss_terms,
+               'loss_terms': loss_terms, '_raster_state': st,
                'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, sk_d_rot, sk_d_scale, p['g_tr'],
                                                  weights, indices)}
         return out, grads
@@ -185,14 +188,18 @@ class HotPath:
                      target_host: Optional[Tensor] = None):
         """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
         the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
-        in the returned tensors.  After a replay has finished, `self.overflowed()` tells whether R exceeded the capacity."""
+        in the returned tensors.  The capacity belongs to THIS graph (nothing process-wide changes; eager calls keep
+        sizing their arena from R).  Every graph owns a pinned header-word buffer (outputs['_header_words']): after a
+        replay has finished, `self.overflowed()` tells whether R exceeded the capacity of any graph captured from this
+        HotPath, and outputs['_raster_state'].overflow_ptr is the device-side flag (skgs_adam_step honours it)."""
         from . import _lib
         from . import diff_gaussian_rasterization as DGR
         kw = dict(arena=arena, after_forward=after_forward, mid_backward=mid_backward, target=target, loss=loss)
         o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, **kw)
         torch.cuda.synchronize(self.device)
         R = int(DGR.last_header_words(self.device)[0])
-        DGR.set_fixed_capacity(int(R * headroom) + 4096)
+        words = DGR.new_header_words()  # pinned memory must be allocated before the capture starts
+        kw.update(fixed_capacity=int(R * headroom) + 4096, header_words=words)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -225,11 +232,17 @@ class HotPath:
                 epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
         torch.cuda.synchronize(self.device)
+        out['_header_words'] = words
+        out['_capacity'] = kw['fixed_capacity']
+        if not hasattr(self, '_graph_words'):
+            self._graph_words = []
+        self._graph_words.append(words)
         return graph, out, grads
 
     def overflowed(self) -> bool:
-        from . import diff_gaussian_rasterization as DGR
-        return bool(DGR.last_header_words(self.device)[3] != 0)
+        """True if the most recent (completed) replay of ANY graph captured from this HotPath exceeded its binning
+        capacity: that replay's image and gradients are invalid.  Call after a synchronisation point."""
+        return any(int(w[3]) != 0 for w in getattr(self, '_graph_words', []))
 
     def zero_grad(self):
         for t in list(self.params.values()) + [self.sp_radius, self.sp_weight]:

@@ -45,16 +45,22 @@ class TrainLoop:
         self._hyper_host = torch.zeros(1 + 2 * len(self.names)).pin_memory()
         self._hyper_dev = torch.zeros(1 + 2 * len(self.names), device=hp.device)
         self.graph = None
+        self._capture_args = None
+        self.recaptures = 0
 
     # ------------------------------------------------------------------------------------------------------ pieces
     def _adam(self, out, grads, grad_scale: float = 1.0, dynamic: bool = False):
         p = self.hp.params
         idx = out['_sk'][-1]
         knn = [idx if (n == 'sp_W' and self.compact_sp_W) else None for n in self.names]
+        # device-side guard: if the render that produced these gradients overflowed its (fixed) binning capacity the
+        # image was empty and the gradients are garbage - the update is skipped on the device, replay() re-captures
+        st = out.get('_raster_state')
         adam_step_raw([p[n].data for n in self.names], [grads[n] for n in self.names],
                       [self.exp_avg[n] for n in self.names], [self.exp_avg_sq[n] for n in self.names],
                       [self.lrs[n] for n in self.names], max(self.iteration, 1), self.betas[0], self.betas[1], self.eps,
-                      grad_scale=grad_scale, knn_indices=knn, dynamic_hyper=self._hyper_dev if dynamic else None)
+                      grad_scale=grad_scale, knn_indices=knn, dynamic_hyper=self._hyper_dev if dynamic else None,
+                      skip_flag_ptr=None if st is None else st.overflow_ptr)
 
     def _set_hyper(self):
         vals = adam_hyper([self.lrs[n] for n in self.names], self.iteration, *self.betas)
@@ -73,6 +79,7 @@ class TrainLoop:
                 headroom: float = 1.5):
         """Capture the whole iteration (uploads -> render -> loss -> backward -> Adam) into one CUDA graph.  The warm-up
         iterations capture needs are undone (parameters and moments restored), so `replay()` x n == `step()` x n."""
+        self._capture_args = dict(view=view, target=target, target_host=target_host, uploads=uploads, headroom=headroom)
         state = [self.hp.params[n].data for n in self.names] + list(self.exp_avg.values()) + \
             list(self.exp_avg_sq.values())
         saved = [t.clone() for t in state]
@@ -91,12 +98,38 @@ class TrainLoop:
         torch.cuda.synchronize(self.hp.device)
         return self.graph
 
+    def overflowed(self) -> bool:
+        """Did the most recent COMPLETED replay exceed the binning capacity the graph was captured with?  (Its Adam
+        update was skipped on the device, so parameters and moments are intact.)"""
+        return self.graph is not None and int(self.out['_header_words'][3]) != 0
+
+    def _recapture(self):
+        """R outgrew the captured capacity (scales / positions moved): capture again with head room over the R that
+        overflowed.  The reference re-sizes its buffers on every call (gaussian_rasterizer_forward.cu:211-213)."""
+        torch.cuda.synchronize(self.hp.device)
+        a = dict(self._capture_args)
+        a['headroom'] = max(float(a['headroom']), 1.5)
+        self.recaptures += 1
+        if self.recaptures > 16:
+            raise RuntimeError('TrainLoop: binning capacity overflowed 16 captures in a row; the scene is diverging')
+        self.capture(**a)
+
     def replay(self, wait: bool = True):
-        """One captured iteration with this iteration's bias corrections / learning rates.  `wait`: block until the
-        previous replay has consumed the pinned hyper-parameter table before overwriting it (off: the table may lag one
-        iteration behind - harmless for throughput measurements, not for exact comparisons)."""
+        """One captured iteration with this iteration's bias corrections / learning rates.
+
+        Overflow of the graph's fixed binning capacity is never silent: the Adam step of such a replay is skipped on
+        the device (skgs_adam_step skip flag) and the host re-captures the graph for the larger R, then repeats the
+        iteration.  With `wait` (default) the previous replay is synchronised first, so the check is exact and
+        replay() x n == step() x n; without it the check looks at whatever replay completed last (the flag persists
+        while the parameters stand still), so detection - and the iteration counter - may lag by the replays in flight:
+        fine for throughput measurements, not for exact comparisons."""
         if wait:
             torch.cuda.current_stream(self.hp.device).synchronize()
+        if self.overflowed():
+            torch.cuda.synchronize(self.hp.device)
+            self.iteration -= 1  # the overflowed replay did not update anything
+            self.out['_header_words'].zero_()
+            self._recapture()
         self.iteration += 1
         self._set_hyper()
         self.graph.replay()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f'{name} declared in include/skgs_b200.h but not exported'
     assert sorted(_lib.check_exports()) == declared  # the ctypes binding covers exactly the header
-    assert L.skgs_abi_version() == 1 and L.skgs_built_for_sm() == 100
+    assert L.skgs_abi_version() == _lib.ABI_VERSION and L.skgs_built_for_sm() == 100
 
 
 def test_built_for_sm100a_only():
@@ -41,14 +41,13 @@ def test_layout_query_is_host_only_and_consistent():
     offs = {n: getattr(lay, n) for n in _lib._LAYOUT_FIELDS}
     assert all(v % 256 == 0 for k, v in offs.items())
     assert offs['header'] == 0 and offs['scan_state'] > 0 and offs['means2D'] > offs['scan_state']
-    assert lay.geom_bytes >= 100000 * (8 + 4 + 24 + 16 + 16 + 1 + 4 + 4 + 48)
+    assert lay.geom_bytes >= 100000 * (8 + 4 + 24 + 16 + 16 + 16 + 1 + 4 + 4 + 48)
     assert lay.binning_bytes >= 1000000 * 24
     assert lay.img_bytes >= 2500 * 8 + 2 * 800 * 800 * 4
-    # 800x800 -> 2500 tiles -> 12 tile bits -> 6 radix passes (even): the sorted lists end in the emission buffers
-    assert offs['keys_sorted'] == offs['keys_unsorted'] and offs['point_list'] == offs['vals_unsorted']
-    # 400x400 -> 625 tiles -> 10 bits -> 6 passes; 160x96 -> 60 tiles -> 6 bits -> 5 passes (odd): separate buffers
-    assert L.skgs_raster_layout_query(10, 160, 96, 1000, C.byref(lay)) == 0
-    assert lay.keys_sorted != lay.keys_unsorted and lay.point_list != lay.vals_unsorted
+    # two physical key / value buffers the radix passes ping-pong between (header.final_buf names the sorted one)
+    assert len({offs['keys_a'], offs['vals_a'], offs['keys_b'], offs['vals_b']}) == 4
+    assert offs['sort_hist'] > offs['vals_b'] and offs['sort_status'] > offs['sort_hist']
+    assert C.sizeof(_lib.RasterHeader) == 128 and _lib.RasterHeader.final_buf.offset == 80
 
 
 def test_errors_are_reported_not_swallowed():
@@ -59,7 +58,7 @@ def test_errors_are_reported_not_swallowed():
     assert L.skgs_raster_layout_query(10, 800, 800, 1 << 27, C.byref(lay)) == -1
     assert b'2^27' in L.skgs_last_error()
     # NULL settings / skeleton are rejected before any CUDA call
-    assert L.skgs_raster_forward_geometry(None, 0, 0, *([None] * 11)) == -1
+    assert L.skgs_raster_forward_geometry(None, 0, 0, *([None] * 10), 0, *([None] * 3)) == -1
     assert b'settings is NULL' in L.skgs_last_error()
     assert L.skgs_fk_lbs_forward(None, 0, *([None] * 8)) == -1
     sk = _lib.Skeleton(M=2000, L=1, root=0, K=5, mode=0, temperature=1.0)
@@ -111,21 +110,21 @@ def test_widening_entry_points_validate_arguments_before_any_device_work():
     assert b'method' in L.skgs_last_error()
 
     table = (_lib.AdamTensor * 1)()
-    assert L.skgs_adam_step(table, 17, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 17, 1, 0.9, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'count 17' in L.skgs_last_error()
-    assert L.skgs_adam_step(table, 1, 0, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 1, 0, 0.9, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'step must be >= 1' in L.skgs_last_error()
-    assert L.skgs_adam_step(table, 1, 1, 1.5, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 1, 1, 1.5, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'hyper-parameters' in L.skgs_last_error()
-    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == 0  # numel 0: nothing to do
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None, None) == 0  # numel 0: nothing to do
     table[0] = _lib.AdamTensor(None, None, None, None, 8, 1e-3, 1e-3, 0, 0, 0, 0, None)
-    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'null pointer' in L.skgs_last_error()
     table[0] = _lib.AdamTensor(1, 1, 1, 1, 8, 1e-3, 1e-3, 4, 4, 0, 0, None)
-    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'split < period' in L.skgs_last_error()
     table[0] = _lib.AdamTensor(1, 1, 1, 1, 8, 1e-3, 1e-3, 0, 0, 4, 5, 1)
-    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None) == -1
+    assert L.skgs_adam_step(table, 1, 1, 0.9, 0.999, 1e-15, 1.0, None, None, None) == -1
     assert b'compact gradient' in L.skgs_last_error()
 
     net = _lib.JointMlp(32, 10, 6, 256, 8, 1 << 4, 11, 1, None)

@@ -29,8 +29,9 @@ def test_binning_products_are_consistent_at_full_size(name):
     torch.cuda.synchronize()
     lay, R, P = st.layout, st.num_rendered, cfg.P
     tiles = ((cfg.W + 15) // 16) * ((cfg.H + 15) // 16)
-    keys = arena_view(st.binning, lay.keys_sorted, torch.int64, R)
-    plist = arena_view(st.binning, lay.point_list, torch.int32, R).long()
+    keys, plist = st.sorted_lists()
+    assert keys.numel() == R
+    plist = plist.long()
     touched = arena_view(st.geom, lay.tiles_touched, torch.int32, P).long()
     ranges = arena_view(st.img, lay.ranges, torch.int32, 2 * tiles).view(tiles, 2).long()
     depths = arena_view(st.geom, lay.depths, torch.float32, P)
@@ -65,6 +66,11 @@ def test_determinism_and_homogeneity_c2():
         a, b = g1[k], g2[k]
         scale = float(a.abs().max())
         assert scale > 0 and float((2 * a - b).abs().max()) <= 2e-5 * scale, k   # only the atomics' order differs
+    # a second backward on the SAME state: the kernels restore their own invariants (accumulators re-zeroed by
+    # preprocess_bwd, work ticket reset), no memset in between
+    g3 = DGR.rasterize_backward(st1, dL)
+    for k in ('means3D', 'shs', 'scales', 'rotations', 'opacities', 'means2D'):
+        assert float((g1[k] - g3[k]).abs().max()) <= 2e-5 * float(g1[k].abs().max()), k
 
 
 def test_forward_only_3m_gaussians_1080p():

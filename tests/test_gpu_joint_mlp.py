@@ -20,13 +20,6 @@ DEV = 'cuda:0'
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.fixture(autouse=True)
-def _reset_capacity_policy():
-    yield
-    from sk_gs_b200 import diff_gaussian_rasterization as DGR
-    DGR.set_fixed_capacity(None)
-
-
 def _rel(a, b):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
@@ -172,13 +165,13 @@ def test_hot_path_with_joint_network():
     c = HotPath(sc, DEV, requires_grad=False, merged_sh=True, joint_mlp=True, head_std=0.02)
     loop_c = TrainLoop(c, lrs={'theta': 1e-5})
     loop_c.capture(0, target, headroom=4.0)
-    cap = DGR._capacity.fixed
+    cap = loop_c.out['_capacity']
     replayed, replay_words = [], []
     for _ in range(3):
         out = loop_c.replay()
         torch.cuda.synchronize()
         replayed.append(float(out['loss_terms'][2]))
-        replay_words.append(DGR.last_header_words(DEV).tolist())
+        replay_words.append(out['_header_words'].tolist())
     info = dict(eager=eager, eager_R=eager_R, replayed=replayed, replay_words=replay_words, capacity=cap)
     assert not c.overflowed(), info
     assert np.abs(np.array(replayed) - np.array(eager)).max() <= 1e-5, info

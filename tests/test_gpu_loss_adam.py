@@ -22,13 +22,6 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 DEV = 'cuda:0'
 
 
-@pytest.fixture(autouse=True)
-def _reset_capacity_policy():
-    yield
-    from sk_gs_b200 import diff_gaussian_rasterization as DGR
-    DGR.set_fixed_capacity(None)  # capture_step pins the binning capacity process-wide
-
-
 def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 

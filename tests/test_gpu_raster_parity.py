@@ -59,7 +59,7 @@ def _geom_arrays(st):
     )
 
 
-CASES = [('c1', 2000, 11), ('c1', None, None), ('c2', 20000, 5)]
+CASES = [('c1', 2000, 11), ('c1', None, None), ('c2', 20000, 5), ('c2', None, None)]
 
 
 @pytest.mark.parametrize('name,P,seed', CASES)
@@ -84,16 +84,32 @@ def test_preprocess_bit_exact(name, P, seed):
     assert st.num_rendered == b.R
 
 
-# debug bit 3 selects the experimental tile-bucketed binning instead of duplicate + onesweep (the default)
-@pytest.mark.parametrize('mode,flags', [('onesweep', 0), ('bucket', 8)])
+def _sorted(st):
+    keys, plist = st.sorted_lists()
+    return keys.cpu().numpy().view(np.uint64), plist.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize('path', ['fused-emission', 'split'])
 @pytest.mark.parametrize('name,P,seed', CASES)
-def test_binning_bit_exact(name, P, seed, mode, flags):
+def test_binning_bit_exact(name, P, seed, path):
+    """Sorted keys, point_list and tile ranges against the oracle's stable sort, through both emission paths: keys
+    emitted by the preprocess kernel (capacity known from the previous call of the shape) and by duplicate_keys_kernel
+    from stored geometry (first call of a shape: R is read between the stages)."""
     sc, net = _inputs(name, P, seed=seed)
     _, _, g, b = _oracle_forward(sc, net)
-    color, _, _, _, st = _gpu_forward(sc, net, debug_flags=flags)
+    key = (0, net['points'].shape[0], sc.cameras[0].W, sc.cameras[0].H)
+    if path == 'split':
+        DGR._capacity.last.pop(key, None)
+    else:
+        DGR._capacity.put(key, b.R)
+    color, _, _, _, st = _gpu_forward(sc, net)
     lay, R = st.layout, b.R
-    keys = arena_view(st.binning, lay.keys_sorted, torch.int64, R).cpu().numpy().view(np.uint64)
-    plist = arena_view(st.binning, lay.point_list, torch.int32, R).cpu().numpy().view(np.uint32)
+    keys, plist = _sorted(st)
+    h = st.header()
+    assert int(h.num_rendered) == R and int(h.overflow) == 0
+    # the depth's sign / exponent byte is the same for every key of these scenes: that pass must have been skipped
+    # (depths lie in [2, 8): top byte 0x40); the pass over the top tile bits is never skipped: it writes the ranges
+    assert int(h.sort_plan[3]) & 1 == 1 and int(h.sort_plan[4]) & 1 == 0
     tiles = b.ranges.shape[0]
     ranges = arena_view(st.img, lay.ranges, torch.int32, 2 * tiles).view(tiles, 2).cpu().numpy().view(np.uint32)
     assert np.array_equal(keys, b.keys)
@@ -104,9 +120,9 @@ def test_binning_bit_exact(name, P, seed, mode, flags):
     assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
 
 
-def test_bucket_sort_out_of_core_and_depth_ties():
-    """Tiles with more than 8192 list entries take the chunked (shared + global) bitonic path; duplicated Gaussians give
-    exactly equal depths, whose order must be ascending Gaussian id (= emission order of the stable reference sort)."""
+def test_sort_long_tiles_and_depth_ties():
+    """Very long tile lists (> 8192 entries) and duplicated Gaussians: exactly equal depths must come out in ascending
+    Gaussian id (= emission order of the stable reference sort)."""
     sc = S.make_scene('c1', P=12000, seed=17)
     cam = sc.cameras[0]
     cam.W, cam.H = 48, 40
@@ -120,11 +136,9 @@ def test_bucket_sort_out_of_core_and_depth_ties():
     assert (b.ranges[:, 1] - b.ranges[:, 0]).max() > 8192
     d = g.depths[b.point_list]
     assert (np.diff(d) == 0).sum() > 1000
-    for flags in (0, 8):
-        color, _, _, _, st = _gpu_forward(sc, net, debug_flags=flags)
-        lay = st.layout
-        plist = arena_view(st.binning, lay.point_list, torch.int32, b.R).cpu().numpy().view(np.uint32)
-        keys = arena_view(st.binning, lay.keys_sorted, torch.int64, b.R).cpu().numpy().view(np.uint64)
+    for _ in range(2):  # first call of the shape: split path; second: keys emitted by the preprocess kernel
+        color, _, _, _, st = _gpu_forward(sc, net)
+        keys, plist = _sorted(st)
         assert np.array_equal(plist, b.point_list) and np.array_equal(keys, b.keys)
         assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
 
@@ -151,7 +165,7 @@ def test_composite_forward(name, P, seed):
 
 
 @pytest.mark.parametrize('name,P,seed,with_aux', [('c1', 2000, 11, True), ('c1', None, None, False),
-                                                  ('c2', 20000, 5, True)])
+                                                  ('c2', 20000, 5, True), ('c2', None, None, False)])
 def test_backward(name, P, seed, with_aux):
     sc, net = _inputs(name, P, seed=seed)
     color, depth, alpha, radii, st = _gpu_forward(sc, net)

@@ -87,3 +87,40 @@ def test_adam_tensor_struct_matches_header():
     # struct skgs_adam_tensor (include/skgs_b200.h): 4 pointers, int64, 2 doubles, 4 int32, pointer
     assert C.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 16 + 16 + 8
     assert _lib.AdamTensor.knn_indices.offset == 72 and _lib.AdamTensor.period.offset == 56
+
+
+def test_adam_is_a_torch_optimizer():
+    """the drop-in must survive what the reference does to its optimizer - isinstance checks and in-place
+    surgery of param_groups / state (networks/gaussian_splatting.py:515-563 `change_optimizer`), lr schedulers,
+    state_dict round trips (checkpoint save / resume)."""
+    a = torch.nn.Parameter(torch.zeros(4, 3))
+    opt = Adam([{'params': [a], 'lr': 0.1, 'name': 'xyz'}], lr=1e-3, eps=1e-15)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5)
+    # state in torch.optim.Adam's format
+    opt.state[a] = {'step': torch.tensor(3.0), 'exp_avg': torch.ones_like(a), 'exp_avg_sq': torch.full_like(a, 2.0)}
+    sd = opt.state_dict()
+    assert set(sd) == {'state', 'param_groups'} and sd['param_groups'][0]['name'] == 'xyz'
+    ref = torch.optim.Adam([{'params': [torch.nn.Parameter(torch.zeros(4, 3))], 'lr': 0.1, 'name': 'xyz'}], eps=1e-15)
+    ref.load_state_dict({'state': sd['state'], 'param_groups': ref.state_dict()['param_groups']})  # interchangeable
+    assert float(next(iter(ref.state.values()))['exp_avg_sq'].mean()) == 2.0
+    opt2 = Adam([{'params': [torch.nn.Parameter(torch.zeros(4, 3))], 'lr': 0.1, 'name': 'xyz'}], eps=1e-15)
+    opt2.load_state_dict(sd)
+    st2 = next(iter(opt2.state.values()))
+    assert float(st2['step']) == 3.0 and torch.equal(st2['exp_avg'], torch.ones(4, 3))
+    sched.step()
+    assert opt.param_groups[0]['lr'] == pytest.approx(0.05)
+    # the surgery change_optimizer(op='prune') performs: new Parameter object, state re-keyed with masked moments
+    keep = torch.tensor([True, False, True, True])
+    group = opt.param_groups[0]
+    old = group['params'][0]
+    stored = opt.state.get(old, None)
+    del opt.state[old]
+    group['params'][0] = torch.nn.Parameter(old[keep].requires_grad_(True))
+    stored['exp_avg'], stored['exp_avg_sq'] = stored['exp_avg'][keep], stored['exp_avg_sq'][keep]
+    opt.state[group['params'][0]] = stored
+    assert opt.state[group['params'][0]]['exp_avg'].shape == (3, 3)
+    opt.zero_grad()
+    opt.step()  # still no gradient: no library call on CPU tensors
+    with pytest.raises(ValueError):
+        Adam([a], lr=-1.0)
