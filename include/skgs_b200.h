@@ -74,7 +74,8 @@ typedef struct skgs_raster_settings {
   int32_t sh_degree;        /* active degree D, 0..3 */
   int32_t quat_wxyz;        /* 1: rotations are (w,x,y,z) (upstream boundary B1); 0: (x,y,z,w) (in-tree boundary B2) */
   int32_t prefiltered;      /* accepted for API parity; culled points are simply skipped */
-  int32_t debug;            /* bit 0: accepted for API parity; bit 1: stop after binning (tests) */
+  int32_t debug;            /* bit 0: accepted for API parity; bit 1: stop after binning (tests); bit 2 (backward): recover
+                               T_final as 1 - (1 - T) like the reference's in-tree extension does (parity tests only) */
   const float* viewmatrix;  /* device [16] */
   const float* projmatrix;  /* device [16] */
   const float* campos;      /* device [3] */
@@ -111,7 +112,7 @@ typedef struct skgs_raster_layout {
   size_t ranges;         /* uint2  [tiles]  [start, end) of every screen tile in the sorted list, (0, 0) if empty */
   size_t n_contrib;      /* uint32 [H*W] */
   size_t final_T;        /* float  [H*W] */
-  size_t tile_order;     /* uint32 [tiles]  tiles by decreasing list length (work order of the compositing kernels) */
+  size_t tile_order;     /* uint4  [tiles]  (tile, start, end, -) by decreasing list length: work order of compositing */
   size_t work_counters;  /* uint32 [2]      work tickets of the forward / backward compositing kernels */
 } skgs_raster_layout;
 
@@ -180,6 +181,21 @@ SKGS_API int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int3
                                   float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
                                   float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream);
 
+/* skgs_raster_backward with the assembly backward (skgs_assemble_backward) fused into its per-Gaussian kernel: the
+ * gradients of the assembled Gaussians are chained on the spot to the canonical parameters - dL_dscaling = dL/dscales *
+ * exp(_scaling), dL_drotation = normalize-backward at (_rotation + d_rot), dL_dopacity = dL/dopacity * s(1 - s) - and
+ * dL/dscales, dL/drotations, dL/dopacity never touch HBM.  SH colours + scale / rotation inputs only (the SK_GS
+ * training step); rotations (x,y,z,w).  The LBS backward then takes dL_dd_xyz = dL_dxyz, dL_dd_rot = dL_drotation,
+ * dL_dd_scale.  d_rot may be NULL (static stage). */
+SKGS_API int skgs_raster_assemble_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                           const float* shs, const float* scales, const float* rotations,
+                                           const int32_t* radii, void* geom, const void* binning, int64_t R_cap,
+                                           const void* img, const float* dL_dcolor, const float* dL_ddepth,
+                                           const float* dL_dalpha, const float* scaling, const float* rotation,
+                                           const float* opacity_logit, const float* d_rot, float* dL_dxyz,
+                                           float* dL_dmeans2D, float* dL_dsh, float* dL_dscaling, float* dL_drotation,
+                                           float* dL_dopacity, float* dL_dd_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Skeleton forward kinematics + linear blend skinning (+ optional output assembly)
  * ------------------------------------------------------------------------------------------------------------- */
@@ -211,9 +227,13 @@ typedef struct skgs_skeleton {
 } skgs_skeleton;
 
 /* Forward.  xyz [P][3] (treated as constant: the reference detaches it, networks/sk_gs.py:1113).
- * Outputs: d_xyz [P][3], d_rot [P][4], d_scale [P][3], sk_T [M][7] (t, q xyzw), weights [P][K], indices int64 [P][K]. */
+ * Outputs: d_xyz [P][3], d_rot [P][4], d_scale [P][3], sk_T [M][7] (t, q xyzw), weights [P][K], indices int64 [P][K].
+ * workspace: device scratch of skgs_fk_lbs_workspace_bytes(M) bytes (the joint table: forward kinematics run ONCE, in
+ * a one-CTA kernel, the per-Gaussian kernel copies the table into shared memory). */
+SKGS_API size_t skgs_fk_lbs_workspace_bytes(int32_t M);
 SKGS_API int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, float* d_xyz, float* d_rot,
-                                 float* d_scale, float* sk_T, float* weights, int64_t* indices, void* stream);
+                                 float* d_scale, float* sk_T, float* weights, int64_t* indices, void* workspace,
+                                 void* stream);
 
 /* Backward.  Incoming: dL_dd_xyz [P][3], dL_dd_rot [P][4], dL_dd_scale [P][3] (any may be NULL = zero), plus optional
  * direct gradients on the auxiliary outputs dL_dsk_T [M][7], dL_dweights [P][K] (NULL = zero).
@@ -222,7 +242,6 @@ SKGS_API int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float
  * the compact form data-parallel ranks exchange, since the KNN pattern is identical on every rank),
  * dL_dsp_radius [M], dL_dsp_weight [M].
  * workspace: device scratch of skgs_fk_lbs_workspace_bytes(M) bytes. */
-SKGS_API size_t skgs_fk_lbs_workspace_bytes(int32_t M);
 SKGS_API int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, const float* sk_T,
                                   const float* weights, const int64_t* indices, const float* dL_dd_xyz,
                                   const float* dL_dd_rot, const float* dL_dd_scale, const float* dL_dsk_T,
@@ -240,6 +259,23 @@ SKGS_API int skgs_assemble_backward(int32_t P, const float* scaling, const float
                                     const float* dL_drotations, const float* dL_dopacities, float* dL_dxyz,
                                     float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_xyz,
                                     float* dL_dd_rot, float* dL_dd_scale, void* stream);
+
+/* The per-Gaussian forward of one view in TWO launches instead of four: forward kinematics once (one CTA), then one
+ * kernel that does K nearest joints + skinning weights + linear blend + output assembly + preprocess + prefix sum + key
+ * emission.  Same device functions and build flags as skgs_fk_lbs_forward -> skgs_assemble_forward ->
+ * skgs_raster_forward_geometry, whose results it reproduces bit for bit (it is an execution plan of the same
+ * operators: networks/sk_gs.py:1109-1150 + :1192,1202-1203 + gaussian_rasterizer_forward.cu:157-215 back to back).
+ * Everything the three backward entry points need is written: weights / indices [P][K], d_rot [P][4], points / scales /
+ * rotations (x,y,z,w) / opacities, sk_T [M][7], the geom arena, radii; keys are emitted into `binning` (R_cap entries):
+ * continue with skgs_raster_forward_render(keys_emitted = 1).  LBS mode, K, joints ... come from `sk`; the skinning
+ * table sk->sp_W is [P][M].  lbs_workspace: skgs_fk_lbs_workspace_bytes(sk->M) bytes. */
+SKGS_API int skgs_deform_forward_geometry(const skgs_skeleton* sk, const skgs_raster_settings* s, int32_t P,
+                                          int32_t M_sh, const float* xyz, const float* scaling, const float* rotation,
+                                          const float* opacity_logit, const float* shs, float* points, float* scales,
+                                          float* rotations, float* opacities, float* d_rot, float* weights,
+                                          int64_t* indices, float* sk_T, void* lbs_workspace, void* geom, int32_t* radii,
+                                          void* binning, int64_t R_cap, void* img, uint32_t* num_rendered_host,
+                                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Widening rows: the step after the path (photometric loss) and the step after that (Adam)

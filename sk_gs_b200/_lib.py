@@ -84,9 +84,13 @@ _SIGNATURES = {
                                      [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'skgs_raster_forward_render': (C.c_int, [C.POINTER(RasterSettings), _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i32] +
                                    [_vp] * 5),
+    'skgs_deform_forward_geometry': (C.c_int, [C.POINTER(Skeleton), C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 5 +
+                                     [_vp] * 7 + [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'skgs_raster_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp, _vp, _i64, _vp] +
                              [_vp] * 12),
-    'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 8),
+    'skgs_raster_assemble_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 5 +
+                                      [_vp, _vp, _i64, _vp] + [_vp] * 3 + [_vp] * 4 + [_vp] * 7 + [_vp]),
+    'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 9),
     'skgs_fk_lbs_workspace_bytes': (C.c_size_t, [_i32]),
     'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),
     'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),

@@ -206,7 +206,7 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   out->ranges = take((size_t)gx * gy * 8);
   out->n_contrib = take((size_t)W * H * 4);
   out->final_T = take((size_t)W * H * 4);
-  out->tile_order = take((size_t)gx * gy * 4);
+  out->tile_order = take((size_t)gx * gy * 16);
   out->work_counters = take(2 * sizeof(uint32_t));
   out->img_bytes = o;
   return SKGS_OK;
@@ -230,6 +230,41 @@ int skgs_raster_forward_geometry(const skgs_raster_settings* s, int32_t P, int32
   return launch_preprocess_scan(rp, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                 (char*)geom, lay, radii, num_rendered_host, (char*)binning, (char*)img,
                                 binning ? R_cap : 0, (cudaStream_t)stream);
+}
+
+int skgs_deform_forward_geometry(const skgs_skeleton* sk, const skgs_raster_settings* s, int32_t P, int32_t M_sh,
+                                 const float* xyz, const float* scaling, const float* rotation,
+                                 const float* opacity_logit, const float* shs, float* points, float* scales,
+                                 float* rotations, float* opacities, float* d_rot, float* weights, int64_t* indices,
+                                 float* sk_T, void* lbs_workspace, void* geom, int32_t* radii, void* binning,
+                                 int64_t R_cap, void* img, uint32_t* num_rendered_host, void* stream) {
+  RasterParams rp;
+  int rc = fill_params(s, P, M_sh, rp);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(sk != nullptr, "skeleton is NULL");
+  SKGS_CHECK_ARG(P > 0, "the fused forward needs P > 0");
+  SKGS_CHECK_ARG(xyz && scaling && rotation && opacity_logit && shs, "NULL canonical parameter");
+  SKGS_CHECK_ARG(points && scales && rotations && opacities && d_rot && weights && indices, "NULL output");
+  SKGS_CHECK_ARG(lbs_workspace && geom && radii && binning && img && R_cap > 0, "NULL workspace / arena");
+  SKGS_CHECK_ARG(s->quat_wxyz == 0, "the fused forward assembles (x,y,z,w) rotations: quat_wxyz must be 0");
+  SKGS_CHECK_ARG(M_sh >= (s->sh_degree + 1) * (s->sh_degree + 1) && M_sh <= 16,
+                 "sh has %d coefficients, degree %d needs %d (max 16)", M_sh, s->sh_degree,
+                 (s->sh_degree + 1) * (s->sh_degree + 1));
+  skgs_raster_layout lay;
+  rc = skgs_raster_layout_query(P, rp.W, rp.H, R_cap, &lay);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_fk_table(sk, sk_T, (float*)lbs_workspace, st);
+  if (rc) return rc;
+  rc = launch_deform_preprocess(rp, sk, (const float*)lbs_workspace, xyz, scaling, rotation, opacity_logit, shs, points,
+                                scales, rotations, opacities, d_rot, weights, indices, (char*)geom, lay, radii,
+                                (char*)binning, (char*)img, R_cap, st);
+  if (rc) return rc;
+  if (num_rendered_host) {
+    auto* hdr = reinterpret_cast<skgs_raster_header*>((char*)geom + lay.header);
+    SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  return SKGS_OK;
 }
 
 // binning (optionally with key emission from the stored geometry) + tile order + compositing
@@ -284,13 +319,14 @@ int skgs_raster_forward(const skgs_raster_settings* s, int32_t P, int32_t M, con
                       num_rendered_host, st);
 }
 
-int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
-                         const float* colors_precomp, const float* scales, const float* rotations,
-                         const float* cov3D_precomp, const int32_t* radii, void* geom, const void* binning,
-                         int64_t R_cap, const void* img, const float* dL_dcolor, const float* dL_ddepth,
-                         const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
-                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
-                         float* dL_dcov3D, void* stream) {
+static int raster_backward_impl(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                const float* shs, const float* colors_precomp, const float* scales,
+                                const float* rotations, const float* cov3D_precomp, const int32_t* radii, void* geom,
+                                const void* binning, int64_t R_cap, const void* img, const float* dL_dcolor,
+                                const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D,
+                                float* dL_dsh, float* dL_dcolors, float* dL_dopacity, float* dL_dscales,
+                                float* dL_drotations, float* dL_dcov3D, const float* const* assemble_in,
+                                float* const* assemble_out, void* stream) {
   RasterParams rp;
   int rc = fill_params(s, P, M, rp);
   if (rc) return rc;
@@ -299,7 +335,8 @@ int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, co
   SKGS_CHECK_ARG(R_cap == 0 || binning != nullptr, "binning arena is NULL");
   SKGS_CHECK_ARG(dL_dmeans3D != nullptr, "dL_dmeans3D is required");
   SKGS_CHECK_ARG(shs == nullptr || dL_dsh != nullptr, "dL_dsh is required when shs is given");
-  SKGS_CHECK_ARG(scales == nullptr || (dL_dscales != nullptr && dL_drotations != nullptr && rotations != nullptr),
+  SKGS_CHECK_ARG(assemble_in != nullptr || scales == nullptr ||
+                     (dL_dscales != nullptr && dL_drotations != nullptr && rotations != nullptr),
                  "dL_dscales / dL_drotations are required when scales/rotations are given");
   SKGS_CHECK_ARG(cov3D_precomp == nullptr || dL_dcov3D != nullptr, "dL_dcov3D is required when cov3D_precomp is given");
   skgs_raster_layout lay;
@@ -307,12 +344,42 @@ int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, co
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_composite_bwd(rp, (char*)geom, (const char*)binning, (const char*)img, lay, dL_dcolor, dL_ddepth,
-                            dL_dalpha, st);
+                            dL_dalpha, (s->debug & 4) ? 1 : 0, st);
   if (rc) return rc;
   uint32_t* bwd_ticket = reinterpret_cast<uint32_t*>((char*)const_cast<void*>(img) + lay.work_counters) + 1;
   return launch_preprocess_bwd(rp, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, (char*)geom,
                                lay, bwd_ticket, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
-                               dL_drotations, dL_dcov3D, st);
+                               dL_drotations, dL_dcov3D, assemble_in, assemble_out, st);
+}
+
+int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* scales, const float* rotations,
+                         const float* cov3D_precomp, const int32_t* radii, void* geom, const void* binning,
+                         int64_t R_cap, const void* img, const float* dL_dcolor, const float* dL_ddepth,
+                         const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
+                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                         float* dL_dcov3D, void* stream) {
+  return raster_backward_impl(s, P, M, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, geom,
+                              binning, R_cap, img, dL_dcolor, dL_ddepth, dL_dalpha, dL_dmeans3D, dL_dmeans2D, dL_dsh,
+                              dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, nullptr, nullptr, stream);
+}
+
+int skgs_raster_assemble_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
+                                  const float* shs, const float* scales, const float* rotations, const int32_t* radii,
+                                  void* geom, const void* binning, int64_t R_cap, const void* img,
+                                  const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                                  const float* scaling, const float* rotation, const float* opacity_logit,
+                                  const float* d_rot, float* dL_dxyz, float* dL_dmeans2D, float* dL_dsh,
+                                  float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_scale,
+                                  void* stream) {
+  SKGS_CHECK_ARG(s != nullptr && s->quat_wxyz == 0, "the fused backward works on (x,y,z,w) rotations: quat_wxyz must be 0");
+  SKGS_CHECK_ARG(shs && scales && rotations && scaling && rotation && opacity_logit, "NULL input");
+  SKGS_CHECK_ARG(dL_dxyz && dL_dsh && dL_dscaling && dL_drotation && dL_dopacity && dL_dd_scale, "NULL output");
+  const float* in[4] = {scaling, rotation, opacity_logit, d_rot};
+  float* out[4] = {dL_dscaling, dL_drotation, dL_dopacity, dL_dd_scale};
+  return raster_backward_impl(s, P, M, means3D, shs, nullptr, scales, rotations, nullptr, radii, geom, binning, R_cap,
+                              img, dL_dcolor, dL_ddepth, dL_dalpha, dL_dxyz, dL_dmeans2D, dL_dsh, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, in, out, stream);
 }
 
 }  // extern "C"

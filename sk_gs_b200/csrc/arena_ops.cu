@@ -78,3 +78,37 @@ extern "C" int skgs_max_i32(int32_t* dst, const int32_t* src, int64_t numel, voi
   }
   return SKGS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// debug: a chain of n dependent trivial kernels, with or without programmatic dependent launch (tools/pdl_probe.py
+// measures what a kernel boundary costs on this box, eagerly and inside a captured graph)
+// ------------------------------------------------------------------------------------------------------------------
+namespace skgs {
+__global__ void pdl_probe_kernel(uint32_t* p) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0 && blockIdx.x == 0) p[0] += 1u;
+}
+}  // namespace skgs
+
+extern "C" __attribute__((visibility("default"))) int skgs_debug_pdl_chain(uint32_t* p, int n, int use_pdl, int grid,
+                                                                          void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n; i++) {
+    if (use_pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(128);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      SKGS_CUDA(cudaLaunchKernelEx(&cfg, skgs::pdl_probe_kernel, p));
+    } else {
+      skgs::pdl_probe_kernel<<<grid, 128, 0, st>>>(p);
+    }
+  }
+  return SKGS_OK;
+}

@@ -170,16 +170,23 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
 int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                    const int32_t* radii, int64_t R_cap, int64_t R_hint, bool emit, uint32_t* num_rendered_host,
                    cudaStream_t st);
+int launch_deform_preprocess(const RasterParams& rp, const skgs_skeleton* sk, const float* table, const float* xyz,
+                             const float* scaling, const float* rotation, const float* opacity_logit, const float* shs,
+                             float* points, float* scales, float* rotations, float* opacities, float* d_rot,
+                             float* weights, int64_t* indices, char* geom, const skgs_raster_layout& lay,
+                             int32_t* radii, char* binning, char* img, int64_t R_cap, cudaStream_t st);
+int launch_fk_table(const skgs_skeleton* sk, float* sk_T, float* table, cudaStream_t st);
 int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st);
 int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                          float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
 int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning, const char* img,
                          const skgs_raster_layout& lay, const float* dL_dcolor, const float* dL_ddepth,
-                         const float* dL_dalpha, cudaStream_t st);
+                         const float* dL_dalpha, int tfinal_via_opacity, cudaStream_t st);
 int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const float* shs, const float* colors_precomp,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           const int32_t* radii, char* geom, const skgs_raster_layout& lay, uint32_t* bwd_ticket,
                           float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
-                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, cudaStream_t st);
+                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, const float* const* assemble_in,
+                          float* const* assemble_out, cudaStream_t st);
 
 }  // namespace skgs

@@ -23,6 +23,8 @@
 //                  atomics per (pixel, Gaussian) (my_ext/_C/src/nerf/gaussian_render.cu:295-338).
 // Semantics: SURVEY.md App. A.6 / A.7 (reference gaussian_render.cu:16-112, 182-341 + bg / depth / alpha terms).
 // Every operation that decides WHICH pairs contribute uses the contraction-proof helpers of common.cuh.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace skgs {
@@ -31,10 +33,19 @@ namespace skgs {
 #define SKGS_CW_WARPS 4
 #endif
 #ifndef SKGS_BWD_MINBLOCKS
-#define SKGS_BWD_MINBLOCKS 6
+#define SKGS_BWD_MINBLOCKS 5
 #endif
 #ifndef SKGS_RSLOTS
 #define SKGS_RSLOTS 6
+#endif
+#ifndef SKGS_FWD_ILP2
+#define SKGS_FWD_ILP2 0
+#endif
+#ifndef SKGS_FWD_CTAS
+#define SKGS_FWD_CTAS 0   // 0: as many CTAs per SM as fit
+#endif
+#ifndef SKGS_BWD_CTAS
+#define SKGS_BWD_CTAS 0
 #endif
 constexpr int CW_WARPS = SKGS_CW_WARPS;     // warps per CTA (independent workers)
 constexpr int CW_THREADS = CW_WARPS * 32;
@@ -59,7 +70,7 @@ __device__ __forceinline__ int length_bin(uint32_t len) {
 }
 
 __global__ void __launch_bounds__(TO_THREADS)
-tile_order_kernel(uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order,
+tile_order_kernel(uint2* __restrict__ ranges, int tiles, uint4* __restrict__ order,
                   uint32_t* __restrict__ counters) {
   __shared__ uint32_t s_hist[TO_BINS];
   __shared__ uint32_t s_base[TO_BINS];
@@ -98,7 +109,7 @@ tile_order_kernel(uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ 
   for (int t = threadIdx.x; t < tiles; t += TO_THREADS) {
     const uint2 r = ranges[t];  // this thread's own write above
     const uint32_t p = atomicAdd(&s_base[length_bin(r.y - r.x)], 1u);
-    order[p] = (uint32_t)t;
+    order[p] = make_uint4((uint32_t)t, r.x, r.y, 0u);  // one 16-byte descriptor per work unit: tile, [start, end)
   }
 }
 
@@ -167,7 +178,10 @@ __device__ __forceinline__ bool footprint_may_hit(const Staged& s, float X0, flo
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// work distribution: one ticket per item, the next item is claimed (and its tile / range loaded) one item ahead
+// work distribution: one global ticket per item; the descriptor (tile, start, end) of ticket / 8 comes from the list
+// tile_order_kernel sorted by decreasing tile length.  (Claiming the NEXT item while the current one runs was tried -
+// profiles/r2_composite_prefetch.txt: it binds the second-longest items to the warps that are busy with the longest
+// ones and the tail of the kernel grows by 10 %.)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ITEM_W = 8, ITEM_H = 4, ITEMS_PER_TILE = (TILE / ITEM_W) * (TILE / ITEM_H);
 
@@ -177,8 +191,8 @@ struct Item {
   uint2 range;
 };
 
-__device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items, const uint32_t* __restrict__ order,
-                                           const uint2* __restrict__ ranges, int lane) {
+__device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items, const uint4* __restrict__ order,
+                                           int lane) {
   Item it;
   uint32_t t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1u);
@@ -186,8 +200,9 @@ __device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items,
   it.tile = 0;
   it.range = make_uint2(0u, 0u);
   if (it.id < num_items) {
-    it.tile = (int)__ldg(order + it.id / ITEMS_PER_TILE);
-    it.range = ranges[it.tile];
+    const uint4 w = __ldg(order + it.id / ITEMS_PER_TILE);
+    it.tile = (int)w.x;
+    it.range = make_uint2(w.y, w.z);
   }
   return it;
 }
@@ -196,9 +211,8 @@ __device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items,
 // forward
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CW_THREADS)
-composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
-                     uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
-                     const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+composite_fwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ order,
+                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
                      const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
@@ -216,9 +230,9 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
   const size_t HW = (size_t)H * W;
   const uint32_t num_items = (uint32_t)tiles * ITEMS_PER_TILE;
 
-  Item nxt_item = claim_item(ticket, num_items, order, ranges, lane);
-  while (nxt_item.id < num_items) {
-    const Item it = nxt_item;
+  while (true) {
+    const Item it = claim_item(ticket, num_items, order, lane);
+    if (it.id >= num_items) break;
     const int sub = (int)(it.id % ITEMS_PER_TILE);
     const int tx = it.tile % gx, ty = it.tile / gx;
     const int X0 = tx * TILE + (sub & 1) * ITEM_W, Y0 = ty * TILE + (sub >> 1) * ITEM_H;
@@ -239,7 +253,6 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
     Staged nxt;
     if (lane < total) gather_id(__ldg(point_list + range.x + lane), G, nxt);
     if (32 + lane < total) id_nxt = __ldg(point_list + range.x + 32 + lane);
-    nxt_item = claim_item(ticket, num_items, order, ranges, lane);  // consumed after this item
     for (int b0 = 0; b0 < total; b0 += 32) {
       if (__all_sync(FULL, !live)) break;
       const int nb = min(32, total - b0);
@@ -252,7 +265,66 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
       __syncwarp();
       if (b0 + 32 + lane < total) gather_id(id_nxt, G, nxt);
       if (b0 + 64 + lane < total) id_nxt = __ldg(point_list + range.x + b0 + 64 + lane);
-      // phase 2: front-to-back over the survivors
+#if SKGS_FWD_ILP2
+      // phase 2: front-to-back over the survivors, TWO per iteration: the gathers from shared memory, the exponents
+      // and the exp() of both are independent and overlap; only the blend (T, colour) is applied in list order.  A
+      // warp runs one item alone and the longest items bound the kernel, so per-warp latency matters, not just issue.
+      while (todo) {
+        const int ja = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const bool two = todo != 0u;
+        const int jb = two ? __ffs(todo) - 1 : ja;
+        todo &= todo - 1;
+        const float4 g0a = g0s[ja], g1a = g1s[ja];
+        const float4 g0b = g0s[jb], g1b = g1s[jb];
+        const float dya = __fsub_rn(g0a.y, pyf), dyb = __fsub_rn(g0b.y, pyf);
+        const float pwa = pair_power(g0a.z, __fsub_rn(g0a.x, pxf), __fmul_rn(g0a.w, dya),
+                                     __fmul_rn(__fmul_rn(g1a.x, dya), dya));
+        const float pwb = pair_power(g0b.z, __fsub_rn(g0b.x, pxf), __fmul_rn(g0b.w, dyb),
+                                     __fmul_rn(__fmul_rn(g1b.x, dyb), dyb));
+        const bool ha = (pwa >= g1a.z) && !(pwa > 0.0f);
+        const bool hb = two && (pwb >= g1b.z) && !(pwb > 0.0f);
+        if (!(ha || hb)) continue;
+        const float aa = fminf(0.99f, __fmul_rn(g1a.y, skgs_exp(pwa)));
+        const float ab = fminf(0.99f, __fmul_rn(g1b.y, skgs_exp(pwb)));
+        if (ha && !(aa < 1.0f / 255.0f)) {
+          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, aa));
+          if (test_T < 0.0001f) {  // this Gaussian is NOT blended; the pixel is finished
+            pxf = PARKED;
+            live = false;
+          } else {
+            const float4 c = cs[ja];
+            const float w = __fmul_rn(aa, T);
+            C0 = __fmaf_rn(c.x, w, C0);
+            C1 = __fmaf_rn(c.y, w, C1);
+            C2 = __fmaf_rn(c.z, w, C2);
+            Dp = __fmaf_rn(c.w, w, Dp);
+            T = test_T;
+            last = (uint32_t)(b0 + ja + 1);
+          }
+        }
+        if (hb && live && !(ab < 1.0f / 255.0f)) {
+          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, ab));
+          if (test_T < 0.0001f) {
+            pxf = PARKED;
+            live = false;
+          } else {
+            const float4 c = cs[jb];
+            const float w = __fmul_rn(ab, T);
+            C0 = __fmaf_rn(c.x, w, C0);
+            C1 = __fmaf_rn(c.y, w, C1);
+            C2 = __fmaf_rn(c.z, w, C2);
+            Dp = __fmaf_rn(c.w, w, Dp);
+            T = test_T;
+            last = (uint32_t)(b0 + jb + 1);
+          }
+        }
+      }
+    }
+#else
+      // phase 2: front-to-back over the survivors.  (Two survivors per iteration - staging reads, exponents and exp()
+      // of both overlapped - was measured: +13 % instructions for no gain, the kernel is issue-bound with 2.5 eligible
+      // warps per scheduler, profiles/r2_composite_ilp.txt; SKGS_FWD_ILP2=1 builds that variant.)
       while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -281,6 +353,7 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
         last = (uint32_t)(b0 + j + 1);
       }
     }
+#endif
     if (inside) {
       const size_t pid = (size_t)py * W + px;
       out_color[pid] = __fmaf_rn(T, bg0, C0);
@@ -297,9 +370,10 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // backward.  Same work items as the forward.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int RSLOTS = SKGS_RSLOTS, RSTRIDE = 33;  // reduction staging: rows of 32 + 1 pad word (conflict free)
+constexpr int RSLOTS = SKGS_RSLOTS, RSTRIDE = 36;  // reduction staging: rows of 32 + 4 pad words (16-byte aligned rows)
 
-// Sum the parked rows (two per lane), leave each row total in the row's pad word, then lane s < n turns slot s into
+// Sum the parked rows (two per lane, eight 16-byte reads each: with a row stride of 36 words the quarter-warps of an
+// LDS.128 hit disjoint banks), leave each row total in the row's first pad word, then lane s < n turns slot s into
 // gradients and flushes it with three 16-byte vector REDs: one RED set per (item, Gaussian).
 // Row order of a slot: S1x S1y Sxx Sxy Syy op r g b [z] with S.. the moments of q = o G dL/dalpha over the pixels:
 //   dL/dmean2D = -(A S1x + B S1y, C S1y + B S1x) * (W/2, H/2),   dL/dconic = -1/2 (Sxx, Sxy, Syy)   (App. A.7)
@@ -308,13 +382,15 @@ __device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id
                                             int lane, float ddelx_dx, float ddely_dy, float* __restrict__ ggrad) {
   __syncwarp();
   for (int r = lane; r < n * RV; r += 32) {
-    const float* row = part + r * RSTRIDE;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float4* row = reinterpret_cast<const float4*>(part + r * RSTRIDE);
+    float4 a = row[0], b = row[1];
 #pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-      s0 += row[k]; s1 += row[k + 1]; s2 += row[k + 2]; s3 += row[k + 3];
+    for (int k = 2; k < 8; k += 2) {
+      const float4 c = row[k], d = row[k + 1];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
     }
-    part[r * RSTRIDE + 32] = (s0 + s1) + (s2 + s3);
+    part[r * RSTRIDE + 32] = ((a.x + b.x) + (a.y + b.y)) + ((a.z + b.z) + (a.w + b.w));
   }
   __syncwarp();
   if (lane < n) {
@@ -337,21 +413,20 @@ __device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id
 // not, and then the depth channel - two accumulators, one reduced value - is not carried at all)
 template <bool AUX>
 __global__ void __launch_bounds__(CW_THREADS, SKGS_BWD_MINBLOCKS)
-composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict__ order,
-                     uint32_t* __restrict__ ticket, const uint2* __restrict__ ranges,
-                     const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+composite_bwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ order,
+                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
                      const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
                      const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth,
-                     const float* __restrict__ dL_dalpha_map, float* __restrict__ ggrad) {
+                     const float* __restrict__ dL_dalpha_map, float* __restrict__ ggrad, int tfinal_via_opacity) {
   constexpr int RV = AUX ? 10 : 9;
   __shared__ float4 s_g0[CW_WARPS][32];
   __shared__ float4 s_g1[CW_WARPS][32];
   __shared__ float4 s_c[CW_WARPS][32];
   // cross-lane reduction through shared memory: every lane parks its RV partial sums of up to RSLOTS surviving
-  // Gaussians (rows of 32 + 1 pad word, conflict free), then the RV*RSLOTS rows are summed two per lane - about 35
-  // instructions per surviving Gaussian instead of 100 for ten 5-step shuffle reductions
-  __shared__ float s_part[CW_WARPS][RSLOTS * RV * RSTRIDE];
+  // Gaussians (rows of 32 + 4 pad words), then the RV*RSLOTS rows are summed two per lane - about 25 instructions per
+  // surviving Gaussian instead of 100 for ten 5-step shuffle reductions
+  __shared__ __align__(16) float s_part[CW_WARPS][RSLOTS * RV * RSTRIDE];
   __shared__ uint32_t s_slot_id[CW_WARPS][RSLOTS];
   __shared__ float4 s_slot_abc[CW_WARPS][RSLOTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -369,9 +444,9 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const uint32_t num_items = (uint32_t)tiles * ITEMS_PER_TILE;
 
-  Item nxt_item = claim_item(ticket, num_items, order, ranges, lane);
-  while (nxt_item.id < num_items) {
-    const Item it = nxt_item;
+  while (true) {
+    const Item it = claim_item(ticket, num_items, order, lane);
+    if (it.id >= num_items) break;
     const int sub = (int)(it.id % ITEMS_PER_TILE);
     const int tx = it.tile % gx, ty = it.tile / gx;
     const int X0 = tx * TILE + (sub & 1) * ITEM_W, Y0 = ty * TILE + (sub >> 1) * ITEM_H;
@@ -383,7 +458,11 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
     const size_t pid = (size_t)py * W + px;
 
     const uint32_t last = inside ? n_contrib[pid] : 0u;
-    const float Tfin = inside ? final_T[pid] : 0.f;
+    float Tfin = inside ? final_T[pid] : 0.f;
+    // test hook (settings.debug bit 2): recover T_final the way the reference's in-tree extension does, from its stored
+    // opacity 1 - T (gaussian_render.cu:215 `T_final = 1.0f - out_opacity`): the cancellation costs up to 1e-4 of
+    // relative accuracy in every gradient.  Off by default: the exact final_T (upstream semantics) is used.
+    if (tfinal_via_opacity) Tfin = __fsub_rn(1.0f, __fsub_rn(1.0f, Tfin));
     float T = Tfin;
     const float dp0 = inside ? dL_dpix[pid] : 0.f;
     const float dp1 = inside ? dL_dpix[HW + pid] : 0.f;
@@ -401,7 +480,6 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
     Staged nxt;
     if ((int)mymax - 1 - lane >= 0) gather_id(__ldg(point_list + range.x + mymax - 1 - lane), G, nxt);
     if ((int)mymax - 33 - lane >= 0) id_nxt = __ldg(point_list + range.x + mymax - 33 - lane);
-    nxt_item = claim_item(ticket, num_items, order, ranges, lane);  // consumed after this item
     for (int top = (int)mymax; top > 0; top -= 32) {
       const int nb = min(32, top);
       const bool may = lane < nb && footprint_may_hit(nxt, fx0, fx0 + (float)(ITEM_W - 1), fy0,
@@ -412,28 +490,12 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
       __syncwarp();
       if (top - 33 - lane >= 0) gather_id(id_nxt, G, nxt);
       if (top - 65 - lane >= 0) id_nxt = __ldg(point_list + range.x + top - 65 - lane);
-      while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t posn = (uint32_t)(top - 1 - j);
-        const float4 g0 = g0s[j];
-        const float4 g1 = g1s[j];
-        const float dx = __fsub_rn(g0.x, pxf), dy = __fsub_rn(g0.y, pyf);
-        const float bdy = __fmul_rn(g0.w, dy);
-        const float cdy2 = __fmul_rn(__fmul_rn(g1.x, dy), dy);
-        const float pw = pair_power(g0.z, dx, bdy, cdy2);
-        float G_ = 0.f, alpha = 0.f;
-        bool valid = (pw >= g1.z) && (posn < last) && !(pw > 0.0f);
-        if (valid) {
-          G_ = skgs_exp(pw);
-          alpha = fminf(0.99f, __fmul_rn(g1.y, G_));
-          valid = !(alpha < 1.0f / 255.0f);
-        }
-        if (!__any_sync(FULL, valid)) continue;
+      // the sequential part of one surviving Gaussian: T, the back-to-front colour recurrence, its 9 (10) partial sums
+      auto apply = [&](bool valid, const float4& g0, const float4& g1, const float4& c, float dx, float dy, float G_,
+                       float alpha) {
         float a_1x = 0.f, a_1y = 0.f, a_xx = 0.f, a_xy = 0.f, a_yy = 0.f, a_op = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f,
               a_z = 0.f;
         if (valid) {
-          const float4 c = cs[j];
           const float inv = __fdividef(1.0f, 1.0f - alpha);
           T = T * inv;
           const float w = alpha * T;
@@ -459,22 +521,50 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
           a_xx = qx * dx; a_xy = qx * dy; a_yy = qy * dy;
         }
         // park the partial sums of this Gaussian in slot `nslots`
-        {
-          float* row = part + nslots * (RV * RSTRIDE) + lane;
-          row[0 * RSTRIDE] = a_1x; row[1 * RSTRIDE] = a_1y; row[2 * RSTRIDE] = a_xx; row[3 * RSTRIDE] = a_xy;
-          row[4 * RSTRIDE] = a_yy; row[5 * RSTRIDE] = a_op; row[6 * RSTRIDE] = a_r; row[7 * RSTRIDE] = a_g;
-          row[8 * RSTRIDE] = a_b;
-          if (AUX) row[9 * RSTRIDE] = a_z;
-          if (lane == 0) {
-            slot_id[nslots] = __float_as_uint(g1.w);
-            slot_abc[nslots] = make_float4(-2.0f * g0.z, -g0.w, -2.0f * g1.x, 0.f);
-          }
+        float* row = part + nslots * (RV * RSTRIDE) + lane;
+        row[0 * RSTRIDE] = a_1x; row[1 * RSTRIDE] = a_1y; row[2 * RSTRIDE] = a_xx; row[3 * RSTRIDE] = a_xy;
+        row[4 * RSTRIDE] = a_yy; row[5 * RSTRIDE] = a_op; row[6 * RSTRIDE] = a_r; row[7 * RSTRIDE] = a_g;
+        row[8 * RSTRIDE] = a_b;
+        if (AUX) row[9 * RSTRIDE] = a_z;
+        if (lane == 0) {
+          slot_id[nslots] = __float_as_uint(g1.w);
+          slot_abc[nslots] = make_float4(-2.0f * g0.z, -g0.w, -2.0f * g1.x, 0.f);
         }
         nslots++;
         if (nslots == RSLOTS) {
           flush_slots<RV>(part, slot_id, slot_abc, nslots, lane, ddelx_dx, ddely_dy, ggrad);
           nslots = 0;
         }
+      };
+      // back to front over the survivors, TWO per iteration: staging reads, exponents and exp() of both overlap, the
+      // recurrences are applied in list order (a warp runs an item alone; the longest items bound the kernel)
+      while (todo) {
+        const int ja = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const bool two = todo != 0u;
+        const int jb = two ? __ffs(todo) - 1 : ja;
+        todo &= todo - 1;
+        const uint32_t posa = (uint32_t)(top - 1 - ja), posb = (uint32_t)(top - 1 - jb);
+        const float4 g0a = g0s[ja], g1a = g1s[ja], ca = cs[ja];
+        const float4 g0b = g0s[jb], g1b = g1s[jb], cb = cs[jb];
+        const float dxa = __fsub_rn(g0a.x, pxf), dya = __fsub_rn(g0a.y, pyf);
+        const float dxb = __fsub_rn(g0b.x, pxf), dyb = __fsub_rn(g0b.y, pyf);
+        const float pwa = pair_power(g0a.z, dxa, __fmul_rn(g0a.w, dya), __fmul_rn(__fmul_rn(g1a.x, dya), dya));
+        const float pwb = pair_power(g0b.z, dxb, __fmul_rn(g0b.w, dyb), __fmul_rn(__fmul_rn(g1b.x, dyb), dyb));
+        bool va = (pwa >= g1a.z) && (posa < last) && !(pwa > 0.0f);
+        bool vb = two && (pwb >= g1b.z) && (posb < last) && !(pwb > 0.0f);
+        float Ga = 0.f, Gb = 0.f, aa = 0.f, ab = 0.f;
+        if (va || vb) {
+          Ga = skgs_exp(pwa);
+          Gb = skgs_exp(pwb);
+          aa = fminf(0.99f, __fmul_rn(g1a.y, Ga));
+          ab = fminf(0.99f, __fmul_rn(g1b.y, Gb));
+          va = va && !(aa < 1.0f / 255.0f);
+          vb = vb && !(ab < 1.0f / 255.0f);
+        }
+        const bool anya = __any_sync(FULL, va), anyb = __any_sync(FULL, vb);
+        if (anya) apply(va, g0a, g1a, ca, dxa, dya, Ga, aa);
+        if (anyb) apply(vb, g0b, g1b, cb, dxb, dyb, Gb, ab);
       }
     }
     if (nslots > 0) {
@@ -487,14 +577,43 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------
-static int persistent_grid(const void* kernel) {
+// Persistent grid = SMs x resident CTAs.  A warp runs one work item alone, and the longest items bound the kernel: their
+// speed is the warp's share of its scheduler's issue slots, so FEWER resident warps can be faster than full occupancy.
+// `max_ctas` (> 0) caps the CTAs per SM by padding the launch with dynamic shared memory (env SKGS_FWD_CTAS / _BWD_CTAS
+// override the built-in choice; tuning: profiles/r2_composite_occupancy.txt).
+struct PersistentCfg {
+  int grid_cap;
+  size_t dyn_smem;
+};
+
+static PersistentCfg persistent_cfg(const void* kernel, int max_ctas) {
   int dev = 0, sms = 0, occ = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CW_THREADS, 0);
   if (sms <= 0) sms = 148;
   if (occ <= 0) occ = 1;
-  return sms * occ;
+  PersistentCfg c{sms * occ, 0};
+  if (max_ctas > 0 && max_ctas < occ) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kernel);
+    int smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const long per_cta = smem_sm / max_ctas - 1024 - (long)fa.sharedSizeBytes - 256;  // 1 KB is reserved per CTA
+    if (per_cta > 0) {
+      c.dyn_smem = (size_t)per_cta / 128 * 128;
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.dyn_smem);
+      int occ2 = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kernel, CW_THREADS, c.dyn_smem);
+      if (occ2 > 0) c.grid_cap = sms * occ2;
+    }
+  }
+  return c;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 static GeomIn geom_in(const char* geom, const skgs_raster_layout& lay) {
@@ -512,7 +631,7 @@ int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layou
   {
     ProfScope prof_("tile_order_kernel", st);
     SKGS_CUDA(launch_pdl(tile_order_kernel, dim3(1), dim3(TO_THREADS), 0, st, reinterpret_cast<uint2*>(img + lay.ranges),
-                         tiles, reinterpret_cast<uint32_t*>(img + lay.tile_order),
+                         tiles, reinterpret_cast<uint4*>(img + lay.tile_order),
                          reinterpret_cast<uint32_t*>(img + lay.work_counters)));
     SKGS_CHECK_LAUNCH("tile_order_kernel");
   }
@@ -523,16 +642,15 @@ int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char
                          float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
   const int tiles = rp.gx * rp.gy;
   if (tiles == 0) return SKGS_OK;
-  static int grid_cap = 0;
-  if (grid_cap == 0) grid_cap = persistent_grid((const void*)composite_fwd_kernel);
+  static PersistentCfg cfg{0, 0};
+  if (cfg.grid_cap == 0) cfg = persistent_cfg((const void*)composite_fwd_kernel, env_int("SKGS_FWD_CTAS", SKGS_FWD_CTAS));
   const int want = (tiles * ITEMS_PER_TILE + CW_WARPS - 1) / CW_WARPS;
-  const int grid = want < grid_cap ? want : grid_cap;
+  const int grid = want < cfg.grid_cap ? want : cfg.grid_cap;
   {
     ProfScope prof_("composite_fwd_kernel", st);
-    SKGS_CUDA(launch_pdl(composite_fwd_kernel, dim3(grid), dim3(CW_THREADS), 0, st, rp.W, rp.H, rp.gx, tiles,
-                         reinterpret_cast<const uint32_t*>(img + lay.tile_order),
+    SKGS_CUDA(launch_pdl(composite_fwd_kernel, dim3(grid), dim3(CW_THREADS), cfg.dyn_smem, st, rp.W, rp.H, rp.gx, tiles,
+                         reinterpret_cast<const uint4*>(img + lay.tile_order),
                          reinterpret_cast<uint32_t*>(img + lay.work_counters),
-                         reinterpret_cast<const uint2*>(img + lay.ranges),
                          reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
                          reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
                          reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
@@ -547,28 +665,29 @@ int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char
 // (and the backward ticket) after consuming them - no memset between the loss and this kernel.
 int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning, const char* img,
                          const skgs_raster_layout& lay, const float* dL_dcolor, const float* dL_ddepth,
-                         const float* dL_dalpha, cudaStream_t st) {
+                         const float* dL_dalpha, int tfinal_via_opacity, cudaStream_t st) {
   float* ggrad = reinterpret_cast<float*>(geom + lay.geom_grads);
   const int tiles = rp.gx * rp.gy;
   if (tiles == 0 || rp.P == 0) return SKGS_OK;
   uint32_t* counters = reinterpret_cast<uint32_t*>(const_cast<char*>(img) + lay.work_counters);
   const bool aux = dL_ddepth != nullptr || dL_dalpha != nullptr;
-  static int grid_cap[2] = {0, 0};
-  if (grid_cap[aux] == 0)
-    grid_cap[aux] = persistent_grid(aux ? (const void*)composite_bwd_kernel<true> : (const void*)composite_bwd_kernel<false>);
+  static PersistentCfg cfg[2] = {{0, 0}, {0, 0}};
+  if (cfg[aux].grid_cap == 0)
+    cfg[aux] = persistent_cfg(aux ? (const void*)composite_bwd_kernel<true> : (const void*)composite_bwd_kernel<false>,
+                              env_int("SKGS_BWD_CTAS", SKGS_BWD_CTAS));
   const int want = (tiles * ITEMS_PER_TILE + CW_WARPS - 1) / CW_WARPS;
-  const int grid = want < grid_cap[aux] ? want : grid_cap[aux];
+  const int grid = want < cfg[aux].grid_cap ? want : cfg[aux].grid_cap;
   {
     ProfScope prof_("composite_bwd_kernel", st);
     auto kern = aux ? composite_bwd_kernel<true> : composite_bwd_kernel<false>;
-    SKGS_CUDA(launch_pdl(kern, dim3(grid), dim3(CW_THREADS), 0, st, rp.W, rp.H, rp.gx, tiles,
-                         reinterpret_cast<const uint32_t*>(img + lay.tile_order), counters + 1,
-                         reinterpret_cast<const uint2*>(img + lay.ranges),
+    SKGS_CUDA(launch_pdl(kern, dim3(grid), dim3(CW_THREADS), cfg[aux].dyn_smem, st, rp.W, rp.H, rp.gx, tiles,
+                         reinterpret_cast<const uint4*>(img + lay.tile_order), counters + 1,
                          reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
                          reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
                          reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
                          reinterpret_cast<const uint32_t*>(img + lay.n_contrib),
-                         reinterpret_cast<const float*>(img + lay.final_T), dL_dcolor, dL_ddepth, dL_dalpha, ggrad));
+                         reinterpret_cast<const float*>(img + lay.final_T), dL_dcolor, dL_ddepth, dL_dalpha, ggrad,
+                         tfinal_via_opacity));
     SKGS_CHECK_LAUNCH("composite_bwd_kernel");
   }
   return SKGS_OK;

@@ -10,11 +10,10 @@
 //   assemble_*        : the element-wise activations of networks/sk_gs.py:1192,1202-1203
 // Semantics: SURVEY.md App. A.1-A.3 (reference networks/sk_gs.py:193-206,751-774,1069-1150; lietorch algebra as in
 // my_ext/_C/include/lie.h:45-64,142-159,228-249).  Quaternions are (x,y,z,w).
-#include "common.cuh"
+#include "deform.cuh"
 
 namespace skgs {
 
-constexpr int MAXK = 8;
 constexpr int FK_THREADS = 256;
 // per-joint accumulator layout of the backward pass
 constexpr int NJ = 19;  // dt[3] dq[4] d(sk_d_rot)[4] d(sk_d_scale)[3] dj(d2)[3] d(radius)[1] d(weight)[1]
@@ -99,16 +98,6 @@ __device__ __forceinline__ Quat local_rotation(const skgs_skeleton& sk, int a) {
   return r;
 }
 
-// shared-memory joint table used by the per-Gaussian loops
-struct JointTable {
-  float* pos;   // [M][3]
-  float* t;     // [M][3]
-  float* R;     // [M][9] row-major
-  float* dq;    // [M][4]
-  float* ds;    // [M][3]
-  float* aux;   // [M][2]  kernel modes: 1/(2 r^2), sigmoid(weight)
-};
-
 // Build sk_T for all joints in shared memory: se[2][M][7] ping-pong.  Returns index of the buffer holding the result.
 __device__ int fk_build(const skgs_skeleton& sk, float* se0, float* se1) {
   const int M = sk.M;
@@ -168,137 +157,70 @@ __device__ __forceinline__ void quat_to_rows(Quat q, float* R) {
   R[6] = 2.f * (x * z - w * y); R[7] = 2.f * (y * z + w * x); R[8] = 1.f - 2.f * (x * x + y * y);
 }
 
-__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+size_t fk_table_smem_bytes(int M) { return (size_t)M * (7 + 7) * sizeof(float); }
 
-size_t fk_fwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 3 + 3 + 9 + 4 + 3 + 2) * sizeof(float); }
-
-template <int KT>  // KT = K as a compile-time constant (1..8): the K-list loops unroll without per-slot K tests
-__global__ void __launch_bounds__(FK_THREADS)
-fk_lbs_fwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, float* __restrict__ d_xyz,
-                  float* __restrict__ d_rot, float* __restrict__ d_scale, float* __restrict__ sk_T,
-                  float* __restrict__ weights, int64_t* __restrict__ indices) {
+// Forward kinematics ONCE per call (one CTA; M <= 1024): local transforms, L pointer-jumping rounds over the
+// binary-lifting table, global transform - in shared memory - then sk_T [M][7] and the joint table the per-Gaussian
+// kernels read (deform.cuh: pos | t | R | d_rot | d_scale | aux, SoA) go to global memory.
+__global__ void __launch_bounds__(1024)
+fk_table_kernel(skgs_skeleton sk, float* __restrict__ sk_T, float* __restrict__ table) {
   extern __shared__ float fsm[];
   const int M = sk.M;
-  constexpr int K = KT;
   float* se0 = fsm;
   float* se1 = se0 + 7 * M;
-  JointTable jt;
-  jt.pos = se1 + 7 * M;
-  jt.t = jt.pos + 3 * M;
-  jt.R = jt.t + 3 * M;
-  jt.dq = jt.R + 9 * M;
-  jt.ds = jt.dq + 4 * M;
-  jt.aux = jt.ds + 3 * M;
+  pdl_wait();
+  pdl_trigger();
   const int res = fk_build(sk, se0, se1);
   const float* T = res == 0 ? se0 : se1;
+  float* pos = table;
+  float* tt = pos + 3 * M;
+  float* R = tt + 3 * M;
+  float* dq = R + 9 * M;
+  float* ds = dq + 4 * M;
+  float* aux = ds + 3 * M;
   for (int a = threadIdx.x; a < M; a += blockDim.x) {
     const float* Ta = T + 7 * a;
-    if (blockIdx.x == 0 && sk_T != nullptr)
+    if (sk_T != nullptr)
       for (int c = 0; c < 7; c++) sk_T[7 * a + c] = Ta[c];
-    jt.pos[3 * a] = sk.joints[3 * a]; jt.pos[3 * a + 1] = sk.joints[3 * a + 1]; jt.pos[3 * a + 2] = sk.joints[3 * a + 2];
-    jt.t[3 * a] = Ta[0]; jt.t[3 * a + 1] = Ta[1]; jt.t[3 * a + 2] = Ta[2];
-    quat_to_rows(q_normalize(load_q(Ta + 3)), jt.R + 9 * a);
-    for (int c = 0; c < 4; c++) jt.dq[4 * a + c] = sk.sk_d_rot[4 * a + c];
-    for (int c = 0; c < 3; c++) jt.ds[3 * a + c] = sk.sk_d_scale[3 * a + c];
+    for (int c = 0; c < 3; c++) pos[3 * a + c] = sk.joints[3 * a + c];
+    for (int c = 0; c < 3; c++) tt[3 * a + c] = Ta[c];
+    quat_to_rows(q_normalize(load_q(Ta + 3)), R + 9 * a);
+    for (int c = 0; c < 4; c++) dq[4 * a + c] = sk.sk_d_rot[4 * a + c];
+    for (int c = 0; c < 3; c++) ds[3 * a + c] = sk.sk_d_scale[3 * a + c];
+    float a0 = 0.f, a1 = 1.f;
     if (sk.mode == SKGS_LBS_KERNEL || sk.mode == SKGS_LBS_WEIGHTED_KERNEL) {
       const float r = expf(sk.sp_radius[a]);
-      jt.aux[2 * a] = 1.0f / (2.0f * r * r);
-      jt.aux[2 * a + 1] = sk.mode == SKGS_LBS_WEIGHTED_KERNEL ? sigmoidf(sk.sp_weight[a]) : 1.0f;
+      a0 = 1.0f / (2.0f * r * r);
+      a1 = sk.mode == SKGS_LBS_WEIGHTED_KERNEL ? sigmoidf(sk.sp_weight[a]) : 1.0f;
     }
+    aux[2 * a] = a0;
+    aux[2 * a + 1] = a1;
   }
-  __syncthreads();
+}
 
+template <int KT>  // KT = K as a compile-time constant (1..8): the K-list lives in registers
+__global__ void __launch_bounds__(FK_THREADS)
+lbs_fwd_kernel(int M, int mode, float temperature, const float* __restrict__ table, const float* __restrict__ sp_W,
+               int P, const float* __restrict__ xyz, float* __restrict__ d_xyz, float* __restrict__ d_rot,
+               float* __restrict__ d_scale, float* __restrict__ weights, int64_t* __restrict__ indices) {
+  extern __shared__ float fsm[];
+  pdl_wait();
+  pdl_trigger();
+  load_joint_table(fsm, table, M);
+  __syncthreads();
+  const JointTable jt = joint_table_view(fsm, M);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-    const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-    float bd[MAXK];
-    int bi[MAXK];
+    const float px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
+    LbsOut<KT> o;
+    lbs_gaussian<KT>(jt, M, mode, temperature, sp_W ? sp_W + (size_t)i * M : nullptr, px, py, pz, o);
+    d_xyz[3 * (size_t)i] = o.dx; d_xyz[3 * (size_t)i + 1] = o.dy; d_xyz[3 * (size_t)i + 2] = o.dz;
+    *reinterpret_cast<float4*>(d_rot + 4 * (size_t)i) = make_float4(o.r0, o.r1, o.r2, o.r3);
+    d_scale[3 * (size_t)i] = o.s0; d_scale[3 * (size_t)i + 1] = o.s1; d_scale[3 * (size_t)i + 2] = o.s2;
 #pragma unroll
-    for (int k = 0; k < MAXK; k++) {
-      bd[k] = k < K ? __int_as_float(0x7f800000) : -1.0f;  // slots >= K never accept
-      bi[k] = 0;
+    for (int k = 0; k < KT; k++) {
+      weights[(size_t)i * KT + k] = o.w[k];
+      indices[(size_t)i * KT + k] = (int64_t)o.idx[k];
     }
-    for (int a = 0; a < M; a++) {
-      const float dx = __fsub_rn(px, jt.pos[3 * a]), dy = __fsub_rn(py, jt.pos[3 * a + 1]),
-                  dz = __fsub_rn(pz, jt.pos[3 * a + 2]);
-      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      // insertion into the ascending K-list (strict '<': ties keep the lower joint index first)
-#pragma unroll
-      for (int k = MAXK - 1; k >= 0; k--) {
-        if (k >= K) continue;
-        if (d2 < bd[k]) {
-          if (k + 1 < K) {
-            bd[k + 1] = bd[k];
-            bi[k + 1] = bi[k];
-          }
-          bd[k] = d2;
-          bi[k] = a;
-        }
-      }
-    }
-    // ---- weights
-    float w[MAXK];
-    float wsum = 0.f;
-    if (sk.mode == SKGS_LBS_W) {
-      float mx = -__int_as_float(0x7f800000);
-#pragma unroll
-      for (int k = 0; k < MAXK; k++)
-        if (k < K) {
-          w[k] = sk.sp_W[(size_t)i * M + bi[k]];
-          mx = fmaxf(mx, w[k]);
-        }
-#pragma unroll
-      for (int k = 0; k < MAXK; k++)
-        if (k < K) {
-          w[k] = expf(w[k] - mx);
-          wsum += w[k];
-        }
-    } else if (sk.mode == SKGS_LBS_DIST) {
-      float mx = -__int_as_float(0x7f800000);
-#pragma unroll
-      for (int k = 0; k < MAXK; k++)
-        if (k < K) {
-          w[k] = -bd[k] / sk.temperature;
-          mx = fmaxf(mx, w[k]);
-        }
-#pragma unroll
-      for (int k = 0; k < MAXK; k++)
-        if (k < K) {
-          w[k] = expf(w[k] - mx);
-          wsum += w[k];
-        }
-    } else {
-#pragma unroll
-      for (int k = 0; k < MAXK; k++)
-        if (k < K) {
-          w[k] = expf(-bd[k] * jt.aux[2 * bi[k]]) * jt.aux[2 * bi[k] + 1] + 1e-7f;
-          wsum += w[k];
-        }
-    }
-    const float winv = 1.0f / wsum;
-    float ox = 0.f, oy = 0.f, oz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < MAXK; k++)
-      if (k < K) {
-        const float wk = w[k] * winv;
-        w[k] = wk;
-        const int a = bi[k];
-        const float* R = jt.R + 9 * a;
-        const float yx = R[0] * px + R[1] * py + R[2] * pz + jt.t[3 * a];
-        const float yy = R[3] * px + R[4] * py + R[5] * pz + jt.t[3 * a + 1];
-        const float yz = R[6] * px + R[7] * py + R[8] * pz + jt.t[3 * a + 2];
-        ox += wk * yx; oy += wk * yy; oz += wk * yz;
-        r0 += wk * jt.dq[4 * a]; r1 += wk * jt.dq[4 * a + 1]; r2 += wk * jt.dq[4 * a + 2]; r3 += wk * jt.dq[4 * a + 3];
-        s0 += wk * jt.ds[3 * a]; s1 += wk * jt.ds[3 * a + 1]; s2 += wk * jt.ds[3 * a + 2];
-      }
-    d_xyz[3 * i] = ox - px; d_xyz[3 * i + 1] = oy - py; d_xyz[3 * i + 2] = oz - pz;
-    *reinterpret_cast<float4*>(d_rot + 4 * i) = make_float4(r0, r1, r2, r3);
-    d_scale[3 * i] = s0; d_scale[3 * i + 1] = s1; d_scale[3 * i + 2] = s2;
-#pragma unroll
-    for (int k = 0; k < MAXK; k++)
-      if (k < K) {
-        weights[(size_t)i * K + k] = w[k];
-        indices[(size_t)i * K + k] = (int64_t)bi[k];
-      }
   }
 }
 
@@ -441,6 +363,17 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
 // slice, and accumulates the contributions to ITS joint in 19 registers that live across all chunks of the persistent
 // CTA.  No atomics until the final cross-slice / cross-CTA reduction.
 // ------------------------------------------------------------------------------------------------------------------
+struct FkBwdOut {   // outputs of the FK backward (any may be NULL)
+  const float* dL_dsk_T_direct;
+  float *dL_djoints, *dL_dsk_r, *dL_dsk_d_rot, *dL_dsk_d_scale, *dL_dg_tr, *dL_dsp_radius, *dL_dsp_weight;
+};
+__device__ __forceinline__ void fk_bwd_body(const skgs_skeleton& sk, const float* __restrict__ jacc,
+                                            const float* __restrict__ dL_dsk_T_direct, float* __restrict__ dL_djoints,
+                                            float* __restrict__ dL_dsk_r, float* __restrict__ dL_dsk_d_rot,
+                                            float* __restrict__ dL_dsk_d_scale, float* __restrict__ dL_dg_tr,
+                                            float* __restrict__ dL_dsp_radius, float* __restrict__ dL_dsp_weight,
+                                            float* ksm);
+
 constexpr int JM_CHUNK = 256;
 constexpr int JM_MAX_M = 256;
 
@@ -466,8 +399,11 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
                   const float* __restrict__ weights, const int64_t* __restrict__ indices,
                   const float* __restrict__ g_dxyz, const float* __restrict__ g_drot,
                   const float* __restrict__ g_dscale, const float* __restrict__ g_w, float* __restrict__ dL_dsp_W,
-                  float* __restrict__ dL_dsp_W_knn, float* __restrict__ jacc /*[M][NJ]*/) {
+                  float* __restrict__ dL_dsp_W_knn, float* __restrict__ jacc /*[M][NJ]*/, uint32_t* __restrict__ done,
+                  FkBwdOut fk) {
   extern __shared__ __align__(16) unsigned char jm_raw[];
+  pdl_wait();
+  pdl_trigger();
   JmChunk& C = *reinterpret_cast<JmChunk*>(jm_raw);
   float* tab = reinterpret_cast<float*>(jm_raw + sizeof(JmChunk));
   const int M = sk.M, K = sk.K;
@@ -655,26 +591,39 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
     const float v = s_acc[k];
     if (v != 0.f) atomicAdd(jacc + k, v);
   }
+  // ---- FK backward as the tail of this kernel: the LAST CTA to get here sees every CTA's per-joint sums and runs the
+  //      level-synchronous sweep through the kinematic chain itself (no second launch, no single-CTA kernel)
+  __shared__ uint32_t s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  fk_bwd_body(sk, jacc, fk.dL_dsk_T_direct, fk.dL_djoints, fk.dL_dsk_r, fk.dL_dsk_d_rot, fk.dL_dsk_d_scale, fk.dL_dg_tr,
+              fk.dL_dsp_radius, fk.dL_dsp_weight, reinterpret_cast<float*>(jm_raw));  // the chunk staging area is free
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // FK backward: one CTA.  Level-synchronous re-evaluation T_root = g, T_a = T_parent o L_a and its reverse sweep.
 // ------------------------------------------------------------------------------------------------------------------
-size_t fk_bwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 7 + 7 + 1) * sizeof(float) + 16; }
+size_t fk_bwd_smem_bytes(int M) { return (size_t)M * (7 + 7 + 7 + 7 + 1) * sizeof(float) + 16; }  // + s_maxdepth
 
-__global__ void __launch_bounds__(1024)
-fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __restrict__ dL_dsk_T_direct,
-              float* __restrict__ dL_djoints, float* __restrict__ dL_dsk_r, float* __restrict__ dL_dsk_d_rot,
-              float* __restrict__ dL_dsk_d_scale, float* __restrict__ dL_dg_tr, float* __restrict__ dL_dsp_radius,
-              float* __restrict__ dL_dsp_weight) {
-  extern __shared__ float ksm[];
+// body of the FK backward, run by ONE CTA (any block size): as the kernel below, or as the tail of lbs_bwd_jm_kernel by
+// the last CTA that finishes (no separate launch)
+__device__ __forceinline__ void fk_bwd_body(const skgs_skeleton& sk, const float* __restrict__ jacc,
+                                            const float* __restrict__ dL_dsk_T_direct, float* __restrict__ dL_djoints,
+                                            float* __restrict__ dL_dsk_r, float* __restrict__ dL_dsk_d_rot,
+                                            float* __restrict__ dL_dsk_d_scale, float* __restrict__ dL_dg_tr,
+                                            float* __restrict__ dL_dsp_radius, float* __restrict__ dL_dsp_weight,
+                                            float* ksm) {
   const int M = sk.M, L = sk.L;
   float* s_L = ksm;              // local transforms [M][7]
   float* s_T = s_L + 7 * M;      // global transforms [M][7]
   float* s_gT = s_T + 7 * M;     // gradient w.r.t. global transforms [M][7]
   float* s_gL = s_gT + 7 * M;    // gradient w.r.t. local transforms [M][7]
   int* s_depth = reinterpret_cast<int*>(s_gL + 7 * M);
-  __shared__ int s_maxdepth;
+  int& s_maxdepth = s_depth[M];
   if (threadIdx.x == 0) s_maxdepth = 0;
   __syncthreads();
   for (int a = threadIdx.x; a < M; a += blockDim.x) {
@@ -692,7 +641,7 @@ fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __r
     float* o = s_L + 7 * a;
     o[0] = j.x + rj.x; o[1] = j.y + rj.y; o[2] = j.z + rj.z; o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
     for (int c = 0; c < 7; c++) {
-      s_gT[7 * a + c] = jacc[NJ * a + c] + (dL_dsk_T_direct ? dL_dsk_T_direct[7 * a + c] : 0.f);
+      s_gT[7 * a + c] = __ldcg(jacc + NJ * a + c) + (dL_dsk_T_direct ? dL_dsk_T_direct[7 * a + c] : 0.f);
       s_gL[7 * a + c] = 0.f;
     }
   }
@@ -762,7 +711,7 @@ fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __r
   // local transform -> joints, sk_r ; plus the direct per-joint sums
   for (int a = threadIdx.x; a < M; a += blockDim.x) {
     const float* gl = s_gL + 7 * a;
-    Vec3 gj = {jacc[NJ * a + 14], jacc[NJ * a + 15], jacc[NJ * a + 16]};
+    Vec3 gj = {__ldcg(jacc + NJ * a + 14), __ldcg(jacc + NJ * a + 15), __ldcg(jacc + NJ * a + 16)};
     Quat gr = {0.f, 0.f, 0.f, 0.f};
     if (a != sk.root) {
       const Quat r = load_q(s_L + 7 * a + 3);
@@ -787,12 +736,24 @@ fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __r
     if (dL_djoints) { dL_djoints[3 * a] = gj.x; dL_djoints[3 * a + 1] = gj.y; dL_djoints[3 * a + 2] = gj.z; }
     if (dL_dsk_r) { dL_dsk_r[4 * a] = gr.x; dL_dsk_r[4 * a + 1] = gr.y; dL_dsk_r[4 * a + 2] = gr.z; dL_dsk_r[4 * a + 3] = gr.w; }
     if (dL_dsk_d_rot)
-      for (int c = 0; c < 4; c++) dL_dsk_d_rot[4 * a + c] = jacc[NJ * a + 7 + c];
+      for (int c = 0; c < 4; c++) dL_dsk_d_rot[4 * a + c] = __ldcg(jacc + NJ * a + 7 + c);
     if (dL_dsk_d_scale)
-      for (int c = 0; c < 3; c++) dL_dsk_d_scale[3 * a + c] = jacc[NJ * a + 11 + c];
-    if (dL_dsp_radius) dL_dsp_radius[a] = jacc[NJ * a + 17];
-    if (dL_dsp_weight) dL_dsp_weight[a] = jacc[NJ * a + 18];
+      for (int c = 0; c < 3; c++) dL_dsk_d_scale[3 * a + c] = __ldcg(jacc + NJ * a + 11 + c);
+    if (dL_dsp_radius) dL_dsp_radius[a] = __ldcg(jacc + NJ * a + 17);
+    if (dL_dsp_weight) dL_dsp_weight[a] = __ldcg(jacc + NJ * a + 18);
   }
+}
+
+__global__ void __launch_bounds__(1024)
+fk_bwd_kernel(skgs_skeleton sk, const float* __restrict__ jacc, const float* __restrict__ dL_dsk_T_direct,
+              float* __restrict__ dL_djoints, float* __restrict__ dL_dsk_r, float* __restrict__ dL_dsk_d_rot,
+              float* __restrict__ dL_dsk_d_scale, float* __restrict__ dL_dg_tr, float* __restrict__ dL_dsp_radius,
+              float* __restrict__ dL_dsp_weight) {
+  extern __shared__ float ksm[];
+  pdl_wait();
+  pdl_trigger();
+  fk_bwd_body(sk, jacc, dL_dsk_T_direct, dL_djoints, dL_dsk_r, dL_dsk_d_rot, dL_dsk_d_scale, dL_dg_tr, dL_dsp_radius,
+              dL_dsp_weight, ksm);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -804,21 +765,22 @@ __global__ void assemble_fwd_kernel(int P, const float* __restrict__ xyz, const 
                                     const float* __restrict__ d_scale, float* __restrict__ points,
                                     float* __restrict__ scales, float* __restrict__ rotations,
                                     float* __restrict__ opacities) {
+  pdl_wait();
+  pdl_trigger();
   const int stride = gridDim.x * blockDim.x;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int e = t0; e < 3 * P; e += stride) {
-    points[e] = xyz[e] + (d_xyz ? d_xyz[e] : 0.f);
-    scales[e] = expf(scaling[e]) + (d_scale ? d_scale[e] : 0.f);
-  }
-  for (int i = t0; i < P; i += stride) {
-    float4 r = *reinterpret_cast<const float4*>(rotation + 4 * i);
-    if (d_rot) {
-      const float4 d = *reinterpret_cast<const float4*>(d_rot + 4 * i);
-      r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
-    }
-    const float n = fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w), 1e-12f);
-    *reinterpret_cast<float4*>(rotations + 4 * i) = make_float4(r.x / n, r.y / n, r.z / n, r.w / n);
-    opacities[i] = sigmoidf(opacity[i]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    const size_t i3 = 3 * (size_t)i;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const Assembled a = assemble_gaussian(
+        xyz[i3], xyz[i3 + 1], xyz[i3 + 2], scaling[i3], scaling[i3 + 1], scaling[i3 + 2],
+        *reinterpret_cast<const float4*>(rotation + 4 * (size_t)i), opacity[i], d_xyz ? d_xyz[i3] : 0.f,
+        d_xyz ? d_xyz[i3 + 1] : 0.f, d_xyz ? d_xyz[i3 + 2] : 0.f,
+        d_rot ? *reinterpret_cast<const float4*>(d_rot + 4 * (size_t)i) : z4, d_scale ? d_scale[i3] : 0.f,
+        d_scale ? d_scale[i3 + 1] : 0.f, d_scale ? d_scale[i3 + 2] : 0.f);
+    points[i3] = a.px; points[i3 + 1] = a.py; points[i3 + 2] = a.pz;
+    scales[i3] = a.sx; scales[i3 + 1] = a.sy; scales[i3 + 2] = a.sz;
+    *reinterpret_cast<float4*>(rotations + 4 * (size_t)i) = make_float4(a.qx, a.qy, a.qz, a.qw);
+    opacities[i] = a.opacity;
   }
 }
 
@@ -895,6 +857,26 @@ static int check_skeleton(const skgs_skeleton* sk, int P) {
   return SKGS_OK;
 }
 
+// sk_T [M][7] (may be NULL) and the joint table (JT_FLOATS * M floats) of one skeleton pose: one CTA
+int launch_fk_table(const skgs_skeleton* sk, float* sk_T, float* table, cudaStream_t st) {
+  int rc = check_skeleton(sk, 0);
+  if (rc) return rc;
+  const size_t smem = fk_table_smem_bytes(sk->M);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    SKGS_CUDA(cudaFuncSetAttribute(fk_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int threads = ((sk->M + 31) / 32) * 32;
+  threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+  {
+    ProfScope prof_("fk_table_kernel", st);
+    SKGS_CUDA(launch_pdl(fk_table_kernel, dim3(1), dim3(threads), smem, st, *sk, sk_T, table));
+    SKGS_CHECK_LAUNCH("fk_table_kernel");
+  }
+  return SKGS_OK;
+}
+
 }  // namespace skgs
 
 using namespace skgs;
@@ -902,26 +884,32 @@ using namespace skgs;
 extern "C" {
 
 int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, float* d_xyz, float* d_rot,
-                        float* d_scale, float* sk_T, float* weights, int64_t* indices, void* stream) {
+                        float* d_scale, float* sk_T, float* weights, int64_t* indices, void* workspace, void* stream) {
   int rc = check_skeleton(sk, P);
   if (rc) return rc;
   SKGS_CHECK_ARG(P >= 0, "P < 0");
   SKGS_CHECK_ARG(P == 0 || (xyz && d_xyz && d_rot && d_scale && weights && indices), "NULL per-Gaussian buffer");
+  SKGS_CHECK_ARG(workspace != nullptr, "workspace (skgs_fk_lbs_workspace_bytes) is required");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = fk_fwd_smem_bytes(sk->M);
+  float* table = reinterpret_cast<float*>(workspace);
+  rc = launch_fk_table(sk, sk_T, table, st);
+  if (rc || P == 0) return rc;
+  const size_t smem = (size_t)sk->M * JT_FLOATS * sizeof(float);
   int grid = (P + FK_THREADS - 1) / FK_THREADS;
-  const int cap = fk_num_sms() * 4;
+  const int cap = fk_num_sms() * 8;
   grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
   {
-    ProfScope prof_("fk_lbs_fwd_kernel", st);
-#define SKGS_FK_CASE(KK)                                                                                              \
-  case KK: {                                                                                                          \
-    static size_t smem_set = 0;                                                                                       \
-    if (smem > 48 * 1024 && smem > smem_set) {                                                                        \
-      SKGS_CUDA(cudaFuncSetAttribute(fk_lbs_fwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      smem_set = smem;                                                                                                \
-    }                                                                                                                 \
-    fk_lbs_fwd_kernel<KK><<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, d_xyz, d_rot, d_scale, sk_T, weights, indices); \
+    ProfScope prof_("lbs_fwd_kernel", st);
+#define SKGS_FK_CASE(KK)                                                                                            \
+  case KK: {                                                                                                        \
+    static size_t smem_set = 0;                                                                                     \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                                      \
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_fwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                              \
+    }                                                                                                               \
+    SKGS_CUDA(launch_pdl(lbs_fwd_kernel<KK>, dim3(grid), dim3(FK_THREADS), smem, st, sk->M, sk->mode,              \
+                         sk->temperature, (const float*)table, sk->sp_W, P, xyz, d_xyz, d_rot, d_scale, weights,   \
+                         indices));                                                                                 \
   } break;
     switch (sk->K) {
       SKGS_FK_CASE(1) SKGS_FK_CASE(2) SKGS_FK_CASE(3) SKGS_FK_CASE(4) SKGS_FK_CASE(5) SKGS_FK_CASE(6) SKGS_FK_CASE(7)
@@ -929,12 +917,15 @@ int skgs_fk_lbs_forward(const skgs_skeleton* sk, int32_t P, const float* xyz, fl
       default: break;
     }
 #undef SKGS_FK_CASE
-    SKGS_CHECK_LAUNCH("fk_lbs_fwd_kernel");
+    SKGS_CHECK_LAUNCH("lbs_fwd_kernel");
   }
   return SKGS_OK;
 }
 
-size_t skgs_fk_lbs_workspace_bytes(int32_t M) { return (size_t)(M > 0 ? M : 1) * NJ * sizeof(float); }
+// forward: the joint table (JT_FLOATS per joint); backward: the per-joint accumulators (NJ per joint) + one ticket word
+size_t skgs_fk_lbs_workspace_bytes(int32_t M) {
+  return (size_t)(M > 0 ? M : 1) * (JT_FLOATS > NJ ? JT_FLOATS : NJ) * sizeof(float) + 64;
+}
 
 int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, const float* sk_T, const float* weights,
                          const int64_t* indices, const float* dL_dd_xyz, const float* dL_dd_rot,
@@ -963,10 +954,14 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
       SKGS_CUDA(cudaMemsetAsync(dL_dsp_W, 0, (size_t)P * sk->M * sizeof(float), st));
     {
       ProfScope prof_("lbs_bwd_kernel", st);
-      lbs_bwd_jm_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
-                                                        dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc);
+      FkBwdOut fk{dL_dsk_T, dL_djoints, dL_dsk_r, dL_dsk_d_rot, dL_dsk_d_scale, dL_dg_tr, dL_dsp_radius, dL_dsp_weight};
+      uint32_t* done = reinterpret_cast<uint32_t*>(jacc + (size_t)sk->M * NJ);  // zeroed with the accumulators above
+      SKGS_CUDA(launch_pdl(lbs_bwd_jm_kernel, dim3(grid), dim3(FK_THREADS), smem, st, *sk, P, xyz, sk_T, weights,
+                           indices, dL_dd_xyz, dL_dd_rot, dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc, done,
+                           fk));
       SKGS_CHECK_LAUNCH("lbs_bwd_jm_kernel");
     }
+    return SKGS_OK;  // the FK backward ran as the tail of the kernel
   } else if (P > 0) {
     const size_t smem = lbs_bwd_smem_bytes(sk->M);
     static size_t smem_set = 0;
@@ -1009,14 +1004,14 @@ int skgs_assemble_forward(int32_t P, const float* xyz, const float* scaling, con
   SKGS_CHECK_ARG(P >= 0, "P < 0");
   if (P == 0) return SKGS_OK;
   SKGS_CHECK_ARG(xyz && scaling && rotation && opacity && points && scales && rotations && opacities, "NULL buffer");
-  int grid = (3 * P + 255) / 256;
+  int grid = (P + 255) / 256;
   const int cap = fk_num_sms() * 8;
   grid = grid > cap ? cap : grid;
   {
     ProfScope prof_("assemble_fwd_kernel", (cudaStream_t)stream);
-    assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, xyz, scaling, rotation, opacity, d_xyz, d_rot, d_scale,
-                                                             points, scales, rotations, opacities);
-  SKGS_CHECK_LAUNCH("assemble_fwd_kernel");
+    SKGS_CUDA(launch_pdl(assemble_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, P, xyz, scaling, rotation,
+                         opacity, d_xyz, d_rot, d_scale, points, scales, rotations, opacities));
+    SKGS_CHECK_LAUNCH("assemble_fwd_kernel");
   }
   return SKGS_OK;
 }

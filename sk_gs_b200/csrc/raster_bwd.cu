@@ -23,6 +23,17 @@ constexpr int NGRAD = 12;  // packed per-Gaussian accumulators (composite.cu): m
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int PB_THREADS = 256;
 
+// Optional fusion of the assembly backward (networks/sk_gs.py:1192,1202-1203 + the activations of
+// networks/gaussian_splatting.py:155-160) into this kernel: with `scaling != NULL` the gradients of the assembled
+// Gaussians are chained on the spot to the canonical parameters and to the LBS outputs, and the intermediate
+// dL/dscales, dL/drotations, dL/dopacity never touch HBM (skgs_assemble_backward as a second kernel otherwise).
+struct AssembleBwd {
+  const float *scaling, *rotation, *opacity, *d_rot;  // _scaling (log), _rotation (raw), _opacity (logit), LBS d_rot or NULL
+  float *dscaling, *drotation, *dopacity;             // gradients of the canonical parameters
+  float* dd_scale;                                    // gradient of the LBS output d_scale (= dL/dscales); d_xyz and
+                                                      // d_rot share dL_dmeans3D / drotation
+};
+
 __global__ void __launch_bounds__(PB_THREADS)
 preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -30,7 +41,7 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
                       const uint8_t* __restrict__ clamped, float* __restrict__ ggrad,
                       uint32_t* __restrict__ bwd_ticket, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales,
-                      float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D) {
+                      float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D, AssembleBwd ab) {
   __shared__ float s_V[16], s_P[16], s_cam[3];
   const int tid = threadIdx.x;
   pdl_wait();
@@ -83,6 +94,11 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
     if (dL_dscales) dL_dscales[3 * i] = dL_dscales[3 * i + 1] = dL_dscales[3 * i + 2] = 0.f;
     if (dL_drotations)
       dL_drotations[4 * i] = dL_drotations[4 * i + 1] = dL_drotations[4 * i + 2] = dL_drotations[4 * i + 3] = 0.f;
+    if (ab.scaling != nullptr) {
+      for (int k = 0; k < 3; k++) ab.dscaling[3 * i + k] = ab.dd_scale[3 * i + k] = 0.f;
+      *reinterpret_cast<float4*>(ab.drotation + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      ab.dopacity[i] = 0.f;
+    }
     return;
   }
   const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
@@ -260,7 +276,8 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   dL_dmeans3D[3 * i + 1] = dmy;
   dL_dmeans3D[3 * i + 2] = dmz;
   // ---- cov3D -> scale, rotation (:357-420)
-  if (scales != nullptr && dL_dscales != nullptr) {
+  if (scales != nullptr && (dL_dscales != nullptr || ab.scaling != nullptr)) {
+    float dsc[3];
     float qr, qx, qy, qz;
     const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * i);
     if (rp.quat_wxyz) {
@@ -289,7 +306,7 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
 #pragma unroll
       for (int r = 0; r < 3; r++) v[r] = dS[r][0] * R[0][k] + dS[r][1] * R[1][k] + dS[r][2] * R[2][k];
       const float dot = R[0][k] * v[0] + R[1][k] * v[1] + R[2][k] * v[2];
-      dL_dscales[3 * i + k] = 2.0f * s[k] * dot;
+      dsc[k] = 2.0f * s[k] * dot;
 #pragma unroll
       for (int r = 0; r < 3; r++) dR[r][k] = 2.0f * s[k] * s[k] * v[r];
     }
@@ -307,7 +324,35 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
       o = make_float4(dqr, dqx, dqy, dqz);
     else
       o = make_float4(dqx, dqy, dqz, dqr);
-    *reinterpret_cast<float4*>(dL_drotations + 4 * i) = o;
+    if (dL_dscales != nullptr) {
+      dL_dscales[3 * i] = dsc[0]; dL_dscales[3 * i + 1] = dsc[1]; dL_dscales[3 * i + 2] = dsc[2];
+    }
+    if (dL_drotations != nullptr) *reinterpret_cast<float4*>(dL_drotations + 4 * i) = o;
+    if (ab.scaling != nullptr) {  // fused assembly backward (same formulas as assemble_bwd_kernel, fk_lbs.cu)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        ab.dscaling[3 * i + k] = dsc[k] * expf(ab.scaling[3 * i + k]);
+        ab.dd_scale[3 * i + k] = dsc[k];
+      }
+      float4 r = *reinterpret_cast<const float4*>(ab.rotation + 4 * i);
+      if (ab.d_rot != nullptr) {
+        const float4 d = *reinterpret_cast<const float4*>(ab.d_rot + 4 * i);
+        r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+      }
+      const float nn = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+      float4 go;
+      if (nn > 1e-12f) {
+        const float inv = 1.0f / nn;
+        const float ux = r.x * inv, uy = r.y * inv, uz = r.z * inv, uw = r.w * inv;
+        const float d = o.x * ux + o.y * uy + o.z * uz + o.w * uw;
+        go = make_float4((o.x - d * ux) * inv, (o.y - d * uy) * inv, (o.z - d * uz) * inv, (o.w - d * uw) * inv);
+      } else {
+        go = make_float4(o.x * 1e12f, o.y * 1e12f, o.z * 1e12f, o.w * 1e12f);
+      }
+      *reinterpret_cast<float4*>(ab.drotation + 4 * i) = go;
+      const float sg = 1.0f / (1.0f + expf(-ab.opacity[i]));
+      ab.dopacity[i] = g[5] * sg * (1.0f - sg);
+    }
   }
 }
 
@@ -315,8 +360,15 @@ int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const fl
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           const int32_t* radii, char* geom, const skgs_raster_layout& lay, uint32_t* bwd_ticket,
                           float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
-                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, cudaStream_t st) {
+                          float* dL_dscales, float* dL_drotations, float* dL_dcov3D, const float* const* assemble_in,
+                          float* const* assemble_out, cudaStream_t st) {
   if (rp.P == 0) return SKGS_OK;
+  AssembleBwd ab = {};
+  if (assemble_in != nullptr) {
+    ab.scaling = assemble_in[0]; ab.rotation = assemble_in[1]; ab.opacity = assemble_in[2]; ab.d_rot = assemble_in[3];
+    ab.dscaling = assemble_out[0]; ab.drotation = assemble_out[1]; ab.dopacity = assemble_out[2];
+    ab.dd_scale = assemble_out[3];
+  }
   (void)colors_precomp;
   const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom + lay.cov3D);
   {
@@ -325,7 +377,7 @@ int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const fl
                          means3D, shs, cov3D_precomp ? nullptr : scales, rotations, cov, radii,
                          reinterpret_cast<const uint8_t*>(geom + lay.clamped),
                          reinterpret_cast<float*>(geom + lay.geom_grads), bwd_ticket, dL_dmeans3D, dL_dmeans2D, dL_dsh,
-                         dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D));
+                         dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, ab));
     SKGS_CHECK_LAUNCH("preprocess_bwd_kernel");
   }
   return SKGS_OK;

@@ -17,7 +17,7 @@
 #endif
 #include <cooperative_groups.h>
 
-#include "common.cuh"
+#include "deform.cuh"
 
 namespace skgs {
 
@@ -348,6 +348,82 @@ __device__ __forceinline__ void finish_emission(int tid, int nthreads, uint32_t*
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Second half of the per-Gaussian forward kernels: block scan of the tile counts, decoupled look-back across CTAs (one
+// warp inspects 32 predecessors per step), then - when EMIT - the warp-cooperative key emission and the radix plan.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool EMIT>
+__device__ __forceinline__ void scan_and_emit(const RasterParams& rp, const Emit& e, int i, int bid, int num_blocks,
+                                              uint32_t* s_warp_sum, uint32_t* s_excl_p, uint32_t* s_flag,
+                                              uint32_t* s_hist, uint32_t* __restrict__ tiles_touched,
+                                              uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ scan_state,
+                                              skgs_raster_header* __restrict__ hdr, const BinningOut& bo) {
+  const int tid = threadIdx.x;
+  if (i < rp.P) tiles_touched[i] = e.cnt;
+  const uint32_t touched = e.cnt;
+
+  // ---- block-inclusive scan of `touched`
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t incl = touched;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  const uint32_t vis_ballot = __ballot_sync(FULL, touched > 0);
+  if (lane == 0 && vis_ballot) atomicAdd(&hdr->num_visible, (uint32_t)__popc(vis_ballot));
+  __syncthreads();
+  uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < PRE_THREADS / 32; w++) {
+    const uint32_t s = s_warp_sum[w];
+    if (w < warp) warp_off += s;
+    block_total += s;
+  }
+  // ---- decoupled look-back across blocks, one warp inspects 32 predecessors per step
+  if (warp == 0) {
+    uint64_t excl = 0;
+    if (bid == 0) {
+      if (lane == 0) st_volatile_u64(&scan_state[0], SCAN_FLAG_INC | (uint64_t)block_total);
+    } else {
+      if (lane == 0) st_volatile_u64(&scan_state[bid], SCAN_FLAG_AGG | (uint64_t)block_total);
+      int j = bid - 1;
+      while (true) {
+        const int jj = j - lane;
+        uint64_t w = SCAN_FLAG_INC;  // lanes before block 0 contribute an inclusive 0
+        if (jj >= 0) {
+          do {
+            w = ld_volatile_u64(&scan_state[jj]);
+          } while ((w >> 62) == 0);
+        }
+        const uint32_t inc_mask = __ballot_sync(FULL, (w >> 62) == 2);
+        // sum values of lanes up to and including the first inclusive one
+        const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+        uint64_t v = (lane <= first_inc) ? (w & SCAN_VAL_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        excl += v;
+        if (inc_mask) break;
+        j -= 32;
+      }
+      if (lane == 0) st_volatile_u64(&scan_state[bid], SCAN_FLAG_INC | (excl + block_total));
+    }
+    if (lane == 0) {
+      *s_excl_p = (uint32_t)excl;
+      if (bid == num_blocks - 1) st_volatile_u32(&hdr->num_rendered, (uint32_t)(excl + block_total));
+    }
+  }
+  __syncthreads();
+  const uint32_t s_excl = *s_excl_p;
+  if (i < rp.P) point_offsets[i] = s_excl + warp_off + incl;
+  if (EMIT) {
+    const uint32_t wtotal = __shfl_sync(FULL, incl, 31);
+    emit_warp(lane, e, (uint32_t)i, incl - touched, s_excl + warp_off, wtotal, rp.gx, bo, s_hist, hdr);
+    finish_emission(tid, PRE_THREADS, s_hist, bo, hdr, (uint32_t)num_blocks, s_flag);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K1: preprocess + fused decoupled-look-back prefix sum (+ key emission and digit histograms when EMIT)
 // ------------------------------------------------------------------------------------------------------------------
 template <bool EMIT>
@@ -407,69 +483,90 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
                             means3D[3 * (size_t)i + 2], opacities[i],
                             cov3D_precomp ? cov3D_precomp + 6 * (size_t)i : nullptr, s0, s1, s2, qx, qy, qz, qr, shs,
                             colors_precomp, go);
-    tiles_touched[i] = e.cnt;
   }
-  const uint32_t touched = e.cnt;
+  scan_and_emit<EMIT>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, &s_flag, s_hist, tiles_touched, point_offsets,
+                      scan_state, hdr, bo);
+}
 
-  // ---- block-inclusive scan of `touched`
-  const int lane = tid & 31, warp = tid >> 5;
-  uint32_t incl = touched;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += n;
+// ------------------------------------------------------------------------------------------------------------------
+// K1f: the whole per-Gaussian forward in ONE kernel - K nearest joints + skinning weights + linear blend (deform.cuh),
+// output assembly, preprocess, prefix sum, key emission.  Replaces lbs_fwd_kernel -> assemble_fwd_kernel ->
+// preprocess_scan_kernel (two 40 B / Gaussian round trips through HBM and two kernel boundaries); the joint table comes
+// from fk_table_kernel.  Same device functions, same flags: bit-identical to the three-kernel path.
+// Outputs the backward needs are still written: weights / indices (LBS), d_rot (assembly), points / scales / rotations
+// (rasterizer), opacities (API parity).
+// ------------------------------------------------------------------------------------------------------------------
+struct DeformIO {
+  int M, mode;
+  float temperature;
+  const float* table;                                   // joint table (fk_table_kernel)
+  const float *xyz, *scaling, *rotation, *opacity, *sp_W;  // canonical parameters
+  float *points, *scales, *rotations, *opacities;       // assembled Gaussians
+  float *d_rot, *weights;                               // kept for the backward
+  int64_t* indices;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(PRE_THREADS)
+deform_preprocess_kernel(RasterParams rp, DeformIO io, const float* __restrict__ shs, GeomOut go,
+                         uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ point_offsets,
+                         uint64_t* __restrict__ scan_state, float4* __restrict__ ggrad,
+                         skgs_raster_header* __restrict__ hdr, int num_blocks, BinningOut bo) {
+  extern __shared__ float s_table[];
+  __shared__ int s_bid;
+  __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
+  __shared__ uint32_t s_excl;
+  __shared__ uint32_t s_flag;
+  __shared__ float s_V[16], s_P[16], s_cam[3];
+  __shared__ uint32_t s_hist[MAX_PASSES * 256];
+  const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0) s_bid = (int)atomicAdd(&hdr->scan_ticket, 1u);
+  if (tid < 16) {
+    s_V[tid] = rp.view[tid];
+    s_P[tid] = rp.proj[tid];
   }
-  if (lane == 31) s_warp_sum[warp] = incl;
-  const uint32_t vis_ballot = __ballot_sync(FULL, touched > 0);
-  if (lane == 0 && vis_ballot) atomicAdd(&hdr->num_visible, (uint32_t)__popc(vis_ballot));
+  if (tid < 3) s_cam[tid] = rp.campos[tid];
+  for (int k = tid; k < bo.passes * 256; k += PRE_THREADS) s_hist[k] = 0;
+  load_joint_table(s_table, io.table, io.M);
   __syncthreads();
-  uint32_t warp_off = 0, block_total = 0;
+  const JointTable jt = joint_table_view(s_table, io.M);
+  const int bid = s_bid;
+  const int i = bid * PRE_THREADS + tid;
+  {  // this CTA's share of the per-forward resets: tile ranges, compositing tickets
+    const int per = (bo.tiles + num_blocks - 1) / num_blocks;
+    for (int t = bid * per + tid; t < min(bo.tiles, (bid + 1) * per); t += PRE_THREADS)
+      bo.ranges[t] = make_uint2(RANGE_UNSET, 0u);
+    if (bid == 0 && tid < 2) bo.counters[tid] = 0u;
+  }
+  Emit e;
+  e.cnt = 0; e.x0 = 0; e.y0 = 0; e.w = 0; e.dbits = 0;
+  if (i < rp.P) {
+    ggrad[3 * (size_t)i] = ggrad[3 * (size_t)i + 1] = ggrad[3 * (size_t)i + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t i3 = 3 * (size_t)i;
+    const float x0 = io.xyz[i3], y0 = io.xyz[i3 + 1], z0 = io.xyz[i3 + 2];
+    LbsOut<KT> o;
+    lbs_gaussian<KT>(jt, io.M, io.mode, io.temperature, io.sp_W ? io.sp_W + (size_t)i * io.M : nullptr, x0, y0, z0, o);
 #pragma unroll
-  for (int w = 0; w < PRE_THREADS / 32; w++) {
-    const uint32_t s = s_warp_sum[w];
-    if (w < warp) warp_off += s;
-    block_total += s;
-  }
-  // ---- decoupled look-back across blocks, one warp inspects 32 predecessors per step
-  if (warp == 0) {
-    uint64_t excl = 0;
-    if (bid == 0) {
-      if (lane == 0) st_volatile_u64(&scan_state[0], SCAN_FLAG_INC | (uint64_t)block_total);
-    } else {
-      if (lane == 0) st_volatile_u64(&scan_state[bid], SCAN_FLAG_AGG | (uint64_t)block_total);
-      int j = bid - 1;
-      while (true) {
-        const int jj = j - lane;
-        uint64_t w = SCAN_FLAG_INC;  // lanes before block 0 contribute an inclusive 0
-        if (jj >= 0) {
-          do {
-            w = ld_volatile_u64(&scan_state[jj]);
-          } while ((w >> 62) == 0);
-        }
-        const uint32_t inc_mask = __ballot_sync(FULL, (w >> 62) == 2);
-        // sum values of lanes up to and including the first inclusive one
-        const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-        uint64_t v = (lane <= first_inc) ? (w & SCAN_VAL_MASK) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        excl += v;
-        if (inc_mask) break;
-        j -= 32;
-      }
-      if (lane == 0) st_volatile_u64(&scan_state[bid], SCAN_FLAG_INC | (excl + block_total));
+    for (int k = 0; k < KT; k++) {
+      io.weights[(size_t)i * KT + k] = o.w[k];
+      io.indices[(size_t)i * KT + k] = (int64_t)o.idx[k];
     }
-    if (lane == 0) {
-      s_excl = (uint32_t)excl;
-      if (bid == num_blocks - 1) st_volatile_u32(&hdr->num_rendered, (uint32_t)(excl + block_total));
-    }
+    const float4 d_rot = make_float4(o.r0, o.r1, o.r2, o.r3);
+    *reinterpret_cast<float4*>(io.d_rot + 4 * (size_t)i) = d_rot;
+    const Assembled a = assemble_gaussian(x0, y0, z0, io.scaling[i3], io.scaling[i3 + 1], io.scaling[i3 + 2],
+                                          *reinterpret_cast<const float4*>(io.rotation + 4 * (size_t)i), io.opacity[i],
+                                          o.dx, o.dy, o.dz, d_rot, o.s0, o.s1, o.s2);
+    io.points[i3] = a.px; io.points[i3 + 1] = a.py; io.points[i3 + 2] = a.pz;
+    io.scales[i3] = a.sx; io.scales[i3 + 1] = a.sy; io.scales[i3 + 2] = a.sz;
+    *reinterpret_cast<float4*>(io.rotations + 4 * (size_t)i) = make_float4(a.qx, a.qy, a.qz, a.qw);
+    io.opacities[i] = a.opacity;
+    e = preprocess_gaussian(rp, s_V, s_P, s_cam, i, a.px, a.py, a.pz, a.opacity, nullptr, rp.mod * a.sx, rp.mod * a.sy,
+                            rp.mod * a.sz, a.qx, a.qy, a.qz, a.qw, shs, nullptr, go);
   }
-  __syncthreads();
-  if (i < rp.P) point_offsets[i] = s_excl + warp_off + incl;
-  if (EMIT) {
-    const uint32_t wtotal = __shfl_sync(FULL, incl, 31);
-    emit_warp(lane, e, (uint32_t)i, incl - touched, s_excl + warp_off, wtotal, rp.gx, bo, s_hist, hdr);
-    finish_emission(tid, PRE_THREADS, s_hist, bo, hdr, (uint32_t)num_blocks, &s_flag);
-  }
+  scan_and_emit<true>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, &s_flag, s_hist, tiles_touched, point_offsets,
+                      scan_state, hdr, bo);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -539,7 +636,7 @@ duplicate_keys_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, 
 #define SKGS_OS_THREADS 256
 #endif
 #ifndef SKGS_OS_ITEMS
-#define SKGS_OS_ITEMS 12
+#define SKGS_OS_ITEMS 24   // 6144 keys per CTA tile: fewer, longer tiles beat more CTAs (shorter look-back chains)
 #endif
 constexpr int OS_THREADS = SKGS_OS_THREADS;
 constexpr int OS_ITEMS = SKGS_OS_ITEMS;
@@ -689,8 +786,9 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
               const uint4 v = ld_volatile_v4(row + q);
               w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
             }
+            // [31:29] tag, [28:27] flag: ready <=> (w >> 27) is tag*4 + 1 (aggregate) or tag*4 + 2 (inclusive)
 #pragma unroll
-            for (int k = 0; k < 32; k++) ready &= ((w[k] >> 29) == tag) && (((w[k] >> 27) & 3u) != 0u);
+            for (int k = 0; k < 32; k++) ready &= ((w[k] >> 27) - (tag * 4u + 1u)) < 2u;
           } while (!ready);
         } else {
 #pragma unroll
@@ -828,6 +926,56 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
   }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  return SKGS_OK;
+}
+
+
+// the fused per-Gaussian forward (K1f); the joint table must have been produced on the same stream (launch_fk_table)
+int launch_deform_preprocess(const RasterParams& rp, const skgs_skeleton* sk, const float* table, const float* xyz,
+                             const float* scaling, const float* rotation, const float* opacity_logit, const float* shs,
+                             float* points, float* scales, float* rotations, float* opacities, float* d_rot,
+                             float* weights, int64_t* indices, char* geom, const skgs_raster_layout& lay,
+                             int32_t* radii, char* binning, char* img, int64_t R_cap, cudaStream_t st) {
+  auto* hdr = reinterpret_cast<skgs_raster_header*>(geom + lay.header);
+  const int nblocks = (rp.P + PRE_THREADS - 1) / PRE_THREADS;
+  SKGS_CHECK_ARG(binning != nullptr && R_cap > 0 && rp.P > 0, "fused forward needs P > 0 and a binning arena");
+  SKGS_CUDA(cudaMemsetAsync(geom + lay.header, 0, lay.means2D - lay.header, st));
+  BinningOut bo = {};
+  int rc = binning_out(rp, binning, img, lay, R_cap, bo);
+  if (rc) return rc;
+  SKGS_CUDA(cudaMemsetAsync(binning + lay.sort_hist, 0, lay.binning_bytes - lay.sort_hist, st));
+  DeformIO io;
+  io.M = sk->M; io.mode = sk->mode; io.temperature = sk->temperature; io.table = table;
+  io.xyz = xyz; io.scaling = scaling; io.rotation = rotation; io.opacity = opacity_logit; io.sp_W = sk->sp_W;
+  io.points = points; io.scales = scales; io.rotations = rotations; io.opacities = opacities;
+  io.d_rot = d_rot; io.weights = weights; io.indices = indices;
+  GeomOut go = geom_out(geom, lay, radii);
+  auto* tt = reinterpret_cast<uint32_t*>(geom + lay.tiles_touched);
+  auto* po = reinterpret_cast<uint32_t*>(geom + lay.point_offsets);
+  auto* ss = reinterpret_cast<uint64_t*>(geom + lay.scan_state);
+  auto* gg = reinterpret_cast<float4*>(geom + lay.geom_grads);
+  const size_t smem = (size_t)sk->M * JT_FLOATS * sizeof(float);
+  {
+    ProfScope prof_("deform_preprocess_kernel", st);
+#define SKGS_DP_CASE(KK)                                                                                             \
+  case KK: {                                                                                                         \
+    static size_t smem_set = 0;                                                                                      \
+    if (smem + 12 * 1024 > 48 * 1024 && smem > smem_set) {                                                           \
+      SKGS_CUDA(cudaFuncSetAttribute(deform_preprocess_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)smem));                                                                    \
+      smem_set = smem;                                                                                               \
+    }                                                                                                                \
+    SKGS_CUDA(launch_pdl(deform_preprocess_kernel<KK>, dim3(nblocks), dim3(PRE_THREADS), smem, st, rp, io, shs, go, \
+                         tt, po, ss, gg, hdr, nblocks, bo));                                                         \
+  } break;
+    switch (sk->K) {
+      SKGS_DP_CASE(1) SKGS_DP_CASE(2) SKGS_DP_CASE(3) SKGS_DP_CASE(4) SKGS_DP_CASE(5) SKGS_DP_CASE(6) SKGS_DP_CASE(7)
+      SKGS_DP_CASE(8)
+      default: SKGS_CHECK_ARG(false, "K=%d out of range", sk->K);
+    }
+#undef SKGS_DP_CASE
+    SKGS_CHECK_LAUNCH("deform_preprocess_kernel");
+  }
   return SKGS_OK;
 }
 

@@ -67,6 +67,12 @@ def new_header_words() -> Tensor:
     return torch.zeros(4, dtype=torch.int32).pin_memory()
 
 
+def capacity_known(device, P: int, W: int, H: int) -> bool:
+    """Has a forward of this shape run on `device` before (so that the binning arena can be sized up front)?"""
+    device = torch.device(device)
+    return _capacity.get((device.index, P, W, H)) is not None
+
+
 def last_header_words(device) -> Tensor:
     """Pinned host int32[4] = {R, num_visible, -, overflow} of the most recent EAGER forward on `device` (valid after
     that forward has completed on the device).  Fixed-capacity (graph) calls write to their own buffer instead."""
@@ -150,8 +156,14 @@ def layout_query(P: int, W: int, H: int, R_cap: int):
 
 def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs=None, colors_precomp=None,
                       scales=None, rotations=None, cov3D_precomp=None, quat_wxyz: bool = True, debug_flags: int = 0,
-                      fixed_capacity: Optional[int] = None, header_words: Optional[Tensor] = None):
+                      fixed_capacity: Optional[int] = None, header_words: Optional[Tensor] = None,
+                      deform: Optional[dict] = None):
     """Non-autograd forward.  Returns (color, depth, alpha, radii, RasterState).
+
+    `deform` (sk_gs_b200.pipeline.HotPath): run the FUSED per-Gaussian forward - skinning + assembly + preprocess + key
+    emission in one kernel (skgs_deform_forward_geometry).  means3D / opacities / scales / rotations are then OUTPUT
+    buffers the kernel fills from deform['xyz' | 'scaling' | 'rotation' | 'opacity'] and the skeleton deform['sk'];
+    needs a known capacity (`fixed_capacity`, or a previous call of the same shape: `capacity_known`).
 
     `fixed_capacity`: size the binning arena for exactly that many (Gaussian, tile) pairs and never look at R on the host
     (no wait at all: CUDA-graph capturable).  It is a property of THIS call - nothing process-wide changes.  If R exceeds
@@ -195,6 +207,18 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
         R_known = None
 
         def geometry(binning, R_cap):
+            if deform is not None:
+                if binning is None:
+                    raise RuntimeError('the fused forward needs a known binning capacity (capacity_known / fixed_capacity)')
+                d = deform
+                _lib.check(L.skgs_deform_forward_geometry(
+                    C.byref(d['sk']), C.byref(s), P, M, d['xyz'].data_ptr(), d['scaling'].data_ptr(),
+                    d['rotation'].data_ptr(), d['opacity'].data_ptr(), _lib.ptr(shs), means3D.data_ptr(),
+                    scales.data_ptr(), rotations.data_ptr(), opacities.data_ptr(), d['d_rot'].data_ptr(),
+                    d['weights'].data_ptr(), d['indices'].data_ptr(), d['sk_T'].data_ptr(), d['workspace'].data_ptr(),
+                    geom.data_ptr(), radii.data_ptr(), binning.data_ptr(), R_cap, img.data_ptr(), words.data_ptr(), st),
+                    'skgs_deform_forward_geometry')
+                return
             _lib.check(L.skgs_raster_forward_geometry(
                 C.byref(s), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(opacities),
                 _lib.ptr(scales), _lib.ptr(rotations), _lib.ptr(cov3D_precomp), geom.data_ptr(), radii.data_ptr(),
@@ -239,9 +263,10 @@ def rasterize_forward(rs: GaussianRasterizationSettings, means3D, opacities, shs
     return color, depth, alpha, radii, state
 
 
-def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, out=None):
+def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, out=None, debug_flags: int = 0):
     """Returns dict of gradients (None where the input was absent).  `out` may supply preallocated, contiguous fp32
-    tensors for any of the keys (e.g. views of a flat all-reduce arena); every output is fully overwritten."""
+    tensors for any of the keys (e.g. views of a flat all-reduce arena); every output is fully overwritten.
+    `debug_flags` are OR-ed into settings.debug for this call (bit 2: the reference extension's T_final recovery)."""
     L = _lib.lib()
     (view, proj, campos, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp) = state.keep
     device = means3D.device
@@ -270,15 +295,61 @@ def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=
         'rotations': None if rotations is None else pick('rotations', P, 4),
         'cov3D_precomp': None if cov3D_precomp is None else pick('cov3D_precomp', P, 6),
     }
+    settings = state.settings
+    if debug_flags:
+        settings = _lib.RasterSettings.from_buffer_copy(bytes(state.settings))
+        settings.debug |= int(debug_flags)
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream
         _lib.check(L.skgs_raster_backward(
-            C.byref(state.settings), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(scales),
+            C.byref(settings), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(colors_precomp), _lib.ptr(scales),
             _lib.ptr(rotations), _lib.ptr(cov3D_precomp), state.radii.data_ptr(), state.geom.data_ptr(),
             state.binning.data_ptr(), state.R_cap, state.img.data_ptr(), dL_dcolor.data_ptr(), _lib.ptr(dL_ddepth),
             _lib.ptr(dL_dalpha), _lib.ptr(g['means3D']), _lib.ptr(g['means2D']), _lib.ptr(g['shs']),
             _lib.ptr(g['colors_precomp']), _lib.ptr(g['opacities']), _lib.ptr(g['scales']), _lib.ptr(g['rotations']),
             _lib.ptr(g['cov3D_precomp']), st), 'skgs_raster_backward')
+    return g
+
+
+def rasterize_assemble_backward(state: RasterState, scaling, rotation, opacity_logit, d_rot, dL_dcolor, dL_ddepth=None,
+                                dL_dalpha=None, out=None, debug_flags: int = 0):
+    """Rasterizer backward with the assembly backward fused into its per-Gaussian kernel
+    (skgs_raster_assemble_backward).  Returns {'xyz' (= dL/dpoints = dL/d_xyz), 'means2D', 'shs', 'scaling', 'rotation'
+    (= dL/d_rot as well), 'opacity', 'dd_scale'}.  `out` may supply preallocated tensors (e.g. arena views)."""
+    L = _lib.lib()
+    (view, proj, campos, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp) = state.keep
+    if shs is None or scales is None or rotations is None:
+        raise RuntimeError('the fused backward needs SH colours and scale / rotation inputs')
+    device = means3D.device
+    P, M = state.P, state.M
+    dL_dcolor = _f32c(dL_dcolor)
+    dL_ddepth = None if dL_ddepth is None else _f32c(dL_ddepth)
+    dL_dalpha = None if dL_dalpha is None else _f32c(dL_dalpha)
+    out = out or {}
+
+    def pick(name, *shape):
+        t = out.get(name)
+        if t is None:
+            return torch.empty(*shape, dtype=torch.float32, device=device)
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == torch.Size(shape).numel(), name
+        return t
+
+    g = {'xyz': pick('xyz', P, 3), 'means2D': pick('means2D', P, 3), 'shs': pick('shs', P, M, 3),
+         'scaling': pick('scaling', P, 3), 'rotation': pick('rotation', P, 4), 'opacity': pick('opacity', P, 1),
+         'dd_scale': pick('dd_scale', P, 3)}
+    settings = state.settings
+    if debug_flags:
+        settings = _lib.RasterSettings.from_buffer_copy(bytes(state.settings))
+        settings.debug |= int(debug_flags)
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(L.skgs_raster_assemble_backward(
+            C.byref(settings), P, M, _lib.ptr(means3D), _lib.ptr(shs), _lib.ptr(scales), _lib.ptr(rotations),
+            state.radii.data_ptr(), state.geom.data_ptr(), state.binning.data_ptr(), state.R_cap, state.img.data_ptr(),
+            dL_dcolor.data_ptr(), _lib.ptr(dL_ddepth), _lib.ptr(dL_dalpha), scaling.data_ptr(), rotation.data_ptr(),
+            opacity_logit.data_ptr(), _lib.ptr(d_rot), g['xyz'].data_ptr(), g['means2D'].data_ptr(),
+            g['shs'].data_ptr(), g['scaling'].data_ptr(), g['rotation'].data_ptr(), g['opacity'].data_ptr(),
+            g['dd_scale'].data_ptr(), st), 'skgs_raster_assemble_backward')
     return g
 
 

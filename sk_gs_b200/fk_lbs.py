@@ -54,11 +54,12 @@ class _FkLbs(torch.autograd.Function):
         sk_T = torch.empty(M, 7, device=device)
         weights = torch.empty(P, K, device=device)
         indices = torch.empty(P, K, dtype=torch.int64, device=device)
+        ws = torch.empty(L.skgs_fk_lbs_workspace_bytes(M), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):
             st = torch.cuda.current_stream(device).cuda_stream
             _lib.check(L.skgs_fk_lbs_forward(C.byref(sk), P, xyz.data_ptr(), d_xyz.data_ptr(), d_rot.data_ptr(),
                                              d_scale.data_ptr(), sk_T.data_ptr(), weights.data_ptr(),
-                                             indices.data_ptr(), st), 'skgs_fk_lbs_forward')
+                                             indices.data_ptr(), ws.data_ptr(), st), 'skgs_fk_lbs_forward')
         ctx.sk = sk
         ctx.keep = (xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, sk_r_delta,
                     sk_T, weights, indices)

@@ -5,14 +5,19 @@ Mirrors what `SkeletonGaussianSplatting.render` does per view in the `sk` stage
 with the joint rotations as leaf parameters by default.  The step before the path (joint-rotation network, SURVEY.md 8f-1,
 `joint_mlp=True`) and the two steps after it - photometric loss (8f-2, networks/sk_gs.py:1524-1529) and Adam (8f-3,
 networks/gaussian_splatting.py:445-453) - are optional stages of `step_grads` / `sk_gs_b200.train.TrainLoop`; the
-benchmarked metric (BASELINE.json) excludes them."""
+benchmarked metric (BASELINE.json) excludes them.
+
+A training step of the reference loops over its views and lets autograd sum their gradients (sk_gs.py:1220); here
+`step_views` / `capture_step` take a LIST of views: every view runs the whole path, its gradients land in a flat arena
+(sk_gs_b200.dist.GradArena) and the arenas of the 2nd, 3rd ... view are folded into the first (skgs_accumulate_f32)."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 from torch import Tensor
 
+from . import _lib
 from .diff_gaussian_rasterization import GaussianRasterizationSettings
 from .fk_lbs import assemble, fk_lbs
 from .renderer import render_gs_offical
@@ -28,6 +33,22 @@ def raster_settings_for(cam: Camera, device, sh_degree: int = 3, scale_modifier:
         image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=cam.bg.to(device),
         scale_modifier=scale_modifier, viewmatrix=cam.viewmatrix.to(device), projmatrix=cam.projmatrix.to(device),
         sh_degree=sh_degree, campos=cam.campos.to(device), prefiltered=False, debug=False)
+
+
+def accumulate_(dst: Tensor, src: Tensor):
+    """dst += src over flat fp32 buffers (libskgs_b200.so, current stream)."""
+    assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+    st = torch.cuda.current_stream(dst.device).cuda_stream
+    _lib.check(_lib.lib().skgs_accumulate_f32(dst.data_ptr(), src.data_ptr(), dst.numel(), st), 'skgs_accumulate_f32')
+    return dst
+
+
+def maximum_(dst: Tensor, src: Tensor):
+    """dst = max(dst, src) over int32 radii (libskgs_b200.so, current stream)."""
+    assert dst.dtype == torch.int32 and src.dtype == torch.int32 and dst.numel() == src.numel()
+    st = torch.cuda.current_stream(dst.device).cuda_stream
+    _lib.check(_lib.lib().skgs_max_i32(dst.data_ptr(), src.data_ptr(), dst.numel(), st), 'skgs_max_i32')
+    return dst
 
 
 class HotPath:
@@ -70,7 +91,9 @@ class HotPath:
         self.parents = scene.parents.to(self.device)
         self.root = scene.root
         self.settings = [raster_settings_for(c, self.device, scene.sh_degree) for c in scene.cameras]
+        self._graph_words: List[Tensor] = []
 
+    # ---------------------------------------------------------------------------------------------- autograd (drop-in)
     def deform(self):
         p = self.params
         if self.mlp is not None:
@@ -88,6 +111,8 @@ class HotPath:
         return dict(points=points, scales=scales, rotations=rotations, opacity=opacity, sh_features=sh), out
 
     def render(self, view: int = 0):
+        """The reference's call sequence through the drop-in operators (fk_lbs -> assemble -> render_gs_offical), with
+        autograd."""
         net_out, sk_out = self.deform()
         out = render_gs_offical(raster_settings=self.settings[view], **net_out)
         out['_sk'] = sk_out
@@ -103,25 +128,31 @@ class HotPath:
             img.backward(dL_dimage)
         return out
 
-    # ------------------------------------------------------------------------------------------------ CUDA graph
-    def step_grads(self, view: int, dL_dimage: Optional[Tensor], compact_sp_W: bool = False, before_backward=None,
-                   arena=None, after_forward=None, mid_backward=None, target: Optional[Tensor] = None,
-                   loss: Optional[dict] = None, fixed_capacity: Optional[int] = None,
-                   header_words: Optional[Tensor] = None):
-        """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
-        nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
-        (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
-        form is cheaper on the host and can be captured into a CUDA graph.
-        With `target` (and `dL_dimage=None`) the upstream gradient comes from the fused L1 + SSIM loss between the rendered
-        image and `target` (`loss` = keyword arguments of losses.image_loss_raw); outputs gain 'loss_terms'."""
+    # --------------------------------------------------------------------------------------- hand-driven (capturable)
+    def forward_raw(self, view: int, fixed_capacity: Optional[int] = None, header_words: Optional[Tensor] = None,
+                    fused: Optional[bool] = None):
+        """FK + LBS -> assembly -> rasterize of one view with the operators driven by hand (no autograd graph).
+        Returns (outputs dict, context for backward_raw).  `fused` (default: whenever possible - LBS mode W and a known
+        binning capacity): the per-Gaussian part runs as ONE kernel (skgs_deform_forward_geometry), bit-identical to
+        the three operator kernels."""
         from . import diff_gaussian_rasterization as DGR
-        from .fk_lbs import (assemble_backward_raw, assemble_forward_raw, fk_lbs_backward_raw, fk_lbs_forward_raw)
+        from .fk_lbs import assemble_forward_raw, fk_lbs_forward_raw
+        rs = self.settings[view]
+        P = self.params['xyz'].shape[0]
+        can_fuse = self.mode == 'W' and P > 0 and (fixed_capacity is not None or DGR.capacity_known(
+            self.device, P, int(rs.image_width), int(rs.image_height)))
+        if fused is None:
+            fused = can_fuse
+        if fused and not can_fuse:
+            raise RuntimeError('fused forward needs LBS mode W and a known binning capacity')
+        if fused:
+            return self._forward_fused(view, fixed_capacity, header_words)
         with torch.no_grad():
             p = self.params
             W = self.mode == 'W'
             cm = None
             if self.mlp is not None:
-                from .deform_net import joint_mlp_backward_raw, joint_mlp_forward_raw
+                from .deform_net import joint_mlp_forward_raw
                 if not hasattr(self, '_mlp_buffers'):
                     self._mlp_buffers = {}
                 (sk_r, sk_d_rot, sk_d_scale), cm = joint_mlp_forward_raw(self.mlp.cfg, p['theta'].data, p['joints'],
@@ -139,25 +170,90 @@ class HotPath:
                                                                    scales=scales, rotations=rotations, quat_wxyz=False,
                                                                    fixed_capacity=fixed_capacity,
                                                                    header_words=header_words)
-            join_after = after_forward(radii) if after_forward is not None else None  # e.g. radii MAX on a side stream
-            if before_backward is not None:
-                before_backward()  # e.g. join the stream that uploads dL_dimage / the target while the forward runs
-            loss_terms = None
-            if target is not None:
-                from .losses import image_loss_raw
-                if not hasattr(self, '_loss_buffers'):
-                    self._loss_buffers = {}
-                loss_terms, dL_dimage = image_loss_raw(color, target, out=self._loss_buffers.setdefault(view, {}),
-                                                       **(loss or {}))
+        out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
+               'loss_terms': None, '_raster_state': st, 'viewspace_points': None,
+               '_sk': (d_xyz, d_rot, d_scale, sk_T, sk_d_rot, sk_d_scale, p['g_tr'], weights, indices)}
+        return out, (cm, c1, c2, st)
+
+    def _forward_fused(self, view: int, fixed_capacity, header_words):
+        """fk_table_kernel + deform_preprocess_kernel + sort + compositing; builds the same backward contexts as the
+        operator-by-operator path."""
+        from . import diff_gaussian_rasterization as DGR
+        from .fk_lbs import _Ctx, _skeleton
+        with torch.no_grad():
+            p, dev = self.params, self.device
+            cm = None
+            if self.mlp is not None:
+                from .deform_net import joint_mlp_forward_raw
+                if not hasattr(self, '_mlp_buffers'):
+                    self._mlp_buffers = {}
+                (sk_r, sk_d_rot, sk_d_scale), cm = joint_mlp_forward_raw(self.mlp.cfg, p['theta'].data, p['joints'],
+                                                                         self.t, out=self._mlp_buffers.setdefault(view, {}))
+            else:
+                sk_r, sk_d_rot, sk_d_scale = p['sk_r'], p['sk_d_rot'], p['sk_d_scale']
+            f = DGR._f32c
+            xyz, joints = f(p['xyz'].detach()), f(p['joints'].detach())
+            sk_r, sk_d_rot, sk_d_scale = f(sk_r.detach()), f(sk_d_rot.detach()), f(sk_d_scale.detach())
+            g_tr = f(p['g_tr'].detach().reshape(-1))
+            sp_W = f(p['sp_W'].detach())
+            scaling, rotation, opacity = f(p['scaling'].detach()), f(p['rotation'].detach()), f(p['opacity'].detach())
+            parents = self.parents.to(device=dev, dtype=torch.int32).contiguous()
+            P, M, K = xyz.shape[0], joints.shape[0], self.K
+            sk = _skeleton(joints, sk_r, sk_d_rot, sk_d_scale, g_tr, parents, self.root, K, 'W', sp_W, None, None, 1.0,
+                           None)
+            new = lambda *s, **kw: torch.empty(*s, device=dev, **kw)  # noqa: E731
+            points, scales, rotations, opac = new(P, 3), new(P, 3), new(P, 4), new(P, 1)
+            d_rot, weights, sk_T = new(P, 4), new(P, K), new(M, 7)
+            indices = new(P, K, dtype=torch.int64)
+            ws = new(_lib.lib().skgs_fk_lbs_workspace_bytes(M), dtype=torch.uint8)
+            sh = p['shs'] if 'shs' in p else torch.cat((p['f_dc'], p['f_rest']), dim=1)
+            deform = dict(sk=sk, xyz=xyz, scaling=scaling, rotation=rotation, opacity=opacity, d_rot=d_rot,
+                          weights=weights, indices=indices, sk_T=sk_T, workspace=ws)
+            color, depth, alpha, radii, st = DGR.rasterize_forward(
+                self.settings[view], points, opac, shs=sh, scales=scales, rotations=rotations, quat_wxyz=False,
+                fixed_capacity=fixed_capacity, header_words=header_words, deform=deform)
+            # contexts of the two operator backwards (same fields their forward would have saved)
+            c1 = _Ctx([False, True, True, True, True, True, True, False, False] + [False] * 6)
+            c1.sk = sk
+            c1.keep = (xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, None, None, parents, None, sk_T, weights,
+                       indices)
+            c1.mode = 'W'
+            c2 = _Ctx([True] * 7)
+            c2.keep = (scaling, rotation, opacity, d_rot)
+            c2.has = (True, True, True)
+        out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
+               'loss_terms': None, '_raster_state': st, 'viewspace_points': None, '_fused': True,
+               '_sk': (None, d_rot, None, sk_T, sk_d_rot, sk_d_scale, p['g_tr'], weights, indices)}
+        return out, (cm, c1, c2, st)
+
+    def backward_raw(self, ctx, dL_dimage: Tensor, compact_sp_W: bool = False, arena=None, mid_backward=None,
+                     fused: bool = True):
+        """The backward calls in reverse.  Returns ({parameter name: gradient}, join for mid_backward).  `fused`
+        (default): the assembly backward runs inside the rasterizer's per-Gaussian backward kernel
+        (skgs_raster_assemble_backward) instead of as a kernel of its own."""
+        from . import diff_gaussian_rasterization as DGR
+        from .fk_lbs import assemble_backward_raw, fk_lbs_backward_raw
+        cm, c1, c2, st = ctx
+        with torch.no_grad():
             # with an arena (sk_gs_b200.dist.GradArena) every final gradient is written straight into its slot of the
             # flat all-reduce buffer: no packing copies before the exchange
             A = (lambda n: arena.view(n) if n in arena.offsets else None) if arena is not None else (lambda n: None)
-            g = DGR.rasterize_backward(st, dL_dimage, out={'means3D': A('xyz'), 'means2D': A('viewspace_points'),
-                                                          'shs': A('shs')})
-            _, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
-                c2, g['means3D'], g['scales'], g['rotations'], g['opacities'],
-                out={'scaling': A('scaling'), 'rotation': A('rotation'), 'opacity': A('opacity')},
-                need=[False, True, True, True, True, True, True])
+            if fused:
+                scaling, rotation, opacity, d_rot = c2.keep
+                ga = DGR.rasterize_assemble_backward(
+                    st, scaling, rotation, opacity, d_rot, dL_dimage,
+                    out={'xyz': A('xyz'), 'means2D': A('viewspace_points'), 'shs': A('shs'), 'scaling': A('scaling'),
+                         'rotation': A('rotation'), 'opacity': A('opacity')})
+                g = {'means3D': ga['xyz'], 'means2D': ga['means2D'], 'shs': ga['shs']}
+                dscaling, drotation, dopacity = ga['scaling'], ga['rotation'], ga['opacity']
+                dd_xyz, dd_rot, dd_scale = ga['xyz'], ga['rotation'], ga['dd_scale']
+            else:
+                g = DGR.rasterize_backward(st, dL_dimage, out={'means3D': A('xyz'), 'means2D': A('viewspace_points'),
+                                                              'shs': A('shs')})
+                _, dscaling, drotation, dopacity, dd_xyz, dd_rot, dd_scale = assemble_backward_raw(
+                    c2, g['means3D'], g['scales'], g['rotations'], g['opacities'],
+                    out={'scaling': A('scaling'), 'rotation': A('rotation'), 'opacity': A('opacity')},
+                    need=[False, True, True, True, True, True, True])
             dxyz = g['means3D']  # d points / d _xyz is the identity
             join_mid = mid_backward() if mid_backward is not None else None  # all rasterizer-side gradients are final
             d_joints, d_sk_r, d_sk_d_rot, d_sk_d_scale, d_g_tr, d_sp_W, d_sp_radius, d_sp_weight = fk_lbs_backward_raw(
@@ -165,6 +261,7 @@ class HotPath:
                 out={n: A(n) for n in ('joints', 'sk_r', 'sk_d_rot', 'sk_d_scale', 'g_tr', 'sp_W')})
             d_theta = None
             if cm is not None:  # back through the joint-rotation network; joints also feed the network input
+                from .deform_net import joint_mlp_backward_raw
                 d_theta, d_joints_net = joint_mlp_backward_raw(cm, d_sk_r, d_sk_d_rot, d_sk_d_scale,
                                                                out={'theta': A('theta')})
                 d_joints.add_(d_joints_net)
@@ -172,39 +269,107 @@ class HotPath:
                  'f_dc': g['shs'][:, :1], 'f_rest': g['shs'][:, 1:], 'sp_W': d_sp_W, 'joints': d_joints, 'sk_r': d_sk_r,
                  'sk_d_rot': d_sk_d_rot, 'sk_d_scale': d_sk_d_scale, 'g_tr': d_g_tr, 'viewspace_points': g['means2D'],
                  'sp_radius': d_sp_radius, 'sp_weight': d_sp_weight, 'theta': d_theta}
+        return grads, join_mid
+
+    def step_grads(self, view: int, dL_dimage: Optional[Tensor], compact_sp_W: bool = False, before_backward=None,
+                   arena=None, after_forward=None, mid_backward=None, target: Optional[Tensor] = None,
+                   loss: Optional[dict] = None, fixed_capacity: Optional[int] = None,
+                   header_words: Optional[Tensor] = None):
+        """forward + backward of one view with the operators driven by hand (no autograd engine, no AccumulateGrad
+        nodes): FK+LBS -> assembly -> rasterize, then the three backward calls in reverse.  Returns
+        (outputs, {parameter name: gradient}); `.grad` is not touched.  Same kernels and same results as step(); this
+        form is cheaper on the host and can be captured into a CUDA graph.
+        With `target` (and `dL_dimage=None`) the upstream gradient comes from the fused L1 + SSIM loss between the rendered
+        image and `target` (`loss` = keyword arguments of losses.image_loss_raw); outputs gain 'loss_terms'."""
+        out, ctx = self.forward_raw(view, fixed_capacity, header_words)
+        join_after = after_forward(out['radii']) if after_forward is not None else None  # e.g. radii MAX, side stream
+        if before_backward is not None:
+            before_backward()  # e.g. join the stream that uploads dL_dimage / the target while the forward runs
+        if target is not None:
+            from .losses import image_loss_raw
+            if not hasattr(self, '_loss_buffers'):
+                self._loss_buffers = {}
+            with torch.no_grad():
+                out['loss_terms'], dL_dimage = image_loss_raw(out['images'], target,
+                                                              out=self._loss_buffers.setdefault(view, {}), **(loss or {}))
+        grads, join_mid = self.backward_raw(ctx, dL_dimage, compact_sp_W, arena, mid_backward)
         if join_after is not None:
             join_after()
         if join_mid is not None:
             join_mid()
-        out = {'images': color, 'depths': depth, 'alpha': alpha, 'radii': radii, 'visibility_filter': None,
-               'loss_terms': loss_terms, '_raster_state': st,
-               'viewspace_points': None, '_sk': (d_xyz, d_rot, d_scale, sk_T, sk_d_rot, sk_d_scale, p['g_tr'],
-                                                 weights, indices)}
         return out, grads
 
-    def capture_step(self, view: int, dL_dimage: Tensor, headroom: float = 1.3, compact_sp_W: bool = False,
-                     uploads=None, dL_host: Optional[Tensor] = None, epilogue=None, arena=None, after_forward=None,
-                     mid_backward=None, target: Optional[Tensor] = None, loss: Optional[dict] = None,
-                     target_host: Optional[Tensor] = None):
-        """Capture forward + backward of one view into a CUDA graph (static shapes, fixed binning capacity = headroom x
-        the R observed in an eager warm-up).  Returns (graph, outputs, grads); replay with graph.replay(), results appear
-        in the returned tensors.  The capacity belongs to THIS graph (nothing process-wide changes; eager calls keep
-        sizing their arena from R).  Every graph owns a pinned header-word buffer (outputs['_header_words']): after a
-        replay has finished, `self.overflowed()` tells whether R exceeded the capacity of any graph captured from this
-        HotPath, and outputs['_raster_state'].overflow_ptr is the device-side flag (skgs_adam_step honours it)."""
-        from . import _lib
+    def step_views(self, views: Sequence[int], dLs: Sequence[Optional[Tensor]], arena, scratch, compact_sp_W: bool = False,
+                   targets: Optional[Sequence[Tensor]] = None, loss: Optional[dict] = None,
+                   capacities: Optional[Sequence[int]] = None, words: Optional[Sequence[Tensor]] = None,
+                   before_backward=None):
+        """One multi-view step on this rank: the whole path for every view in `views`, gradients SUMMED in `arena`
+        (view 0 writes its slots directly, view v > 0 writes `scratch` - an arena of the same layout - which is then
+        folded in), screen radii MAXed.  Returns (outputs of the last view with 'radii' = max over views, grads = views
+        of `arena`)."""
+        assert len(views) >= 1 and arena is not None
+        radii_max = None
+        out = None
+        for k, v in enumerate(views):
+            a = arena if k == 0 else scratch
+            out, _ = self.step_grads(v, dLs[k], compact_sp_W, arena=a, target=None if targets is None else targets[k],
+                                     loss=loss, fixed_capacity=None if capacities is None else capacities[k],
+                                     header_words=None if words is None else words[k],
+                                     before_backward=before_backward if k == 0 else None)
+            if k == 0:
+                radii_max = out['radii']
+            else:
+                accumulate_(arena.flat, scratch.flat)
+                maximum_(radii_max, out['radii'])
+        out = dict(out)
+        out['radii'] = radii_max
+        return out, arena.unpack()
+
+    # ------------------------------------------------------------------------------------------------ CUDA graphs
+    def measure_capacity(self, view: int, headroom: float) -> int:
+        """Binning capacity for a captured graph of `view`: headroom x the R of an eager forward at the current
+        parameters (+ slack)."""
         from . import diff_gaussian_rasterization as DGR
-        kw = dict(arena=arena, after_forward=after_forward, mid_backward=mid_backward, target=target, loss=loss)
-        o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, **kw)
+        self.forward_raw(view, fused=False)
         torch.cuda.synchronize(self.device)
-        R = int(DGR.last_header_words(self.device)[0])
-        words = DGR.new_header_words()  # pinned memory must be allocated before the capture starts
-        kw.update(fixed_capacity=int(R * headroom) + 4096, header_words=words)
+        R = int(DGR.last_header_words(self.device)[0]) & 0xffffffff
+        return int(R * headroom) + 4096
+
+    def capture_step(self, view: Union[int, Sequence[int]], dL_dimage, headroom: float = 1.3,
+                     compact_sp_W: bool = False, uploads=None, dL_host=None, epilogue=None, arena=None,
+                     after_forward=None, mid_backward=None, target=None, loss: Optional[dict] = None,
+                     target_host=None, scratch=None):
+        """Capture forward + backward of one view - or of a LIST of views (multi-view step, needs `arena` + `scratch`;
+        `dL_dimage` / `target` / `dL_host` / `target_host` are then lists) - into a CUDA graph: static shapes, fixed
+        binning capacity per view = headroom x the R observed in an eager warm-up.  Returns (graph, outputs, grads);
+        replay with graph.replay(), results appear in the returned tensors.  The capacities belong to THIS graph (nothing
+        process-wide changes; eager calls keep sizing their arena from R).  Every captured view owns a pinned
+        header-word buffer (outputs['_header_words'], a list for several views): after a replay has finished,
+        `self.overflowed()` tells whether R exceeded the capacity of any graph captured from this HotPath, and
+        outputs['_raster_state'].overflow_ptr is the device-side flag (skgs_adam_step honours it)."""
+        from . import diff_gaussian_rasterization as DGR
+        multi = not isinstance(view, int)
+        views = list(view) if multi else [view]
+        as_list = (lambda x: list(x) if multi else [x])
+        dLs, targets = as_list(dL_dimage), (None if target is None else as_list(target))
+        dL_hosts = [None] * len(views) if dL_host is None else as_list(dL_host)
+        target_hosts = [None] * len(views) if target_host is None else as_list(target_host)
+        caps = [self.measure_capacity(v, headroom) for v in views]
+        words = [DGR.new_header_words() for _ in views]  # pinned memory must be allocated before the capture starts
+
+        def run(before_backward=None):
+            if multi:
+                return self.step_views(views, dLs, arena, scratch, compact_sp_W, targets, loss, caps, words,
+                                       before_backward)
+            return self.step_grads(views[0], dLs[0], compact_sp_W, arena=arena, after_forward=after_forward,
+                                   mid_backward=mid_backward, target=None if targets is None else targets[0], loss=loss,
+                                   fixed_capacity=caps[0], header_words=words[0], before_backward=before_backward)
+
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                o_, g_ = self.step_grads(view, dL_dimage, compact_sp_W, **kw)
+                o_, g_ = run()
                 if epilogue is not None:
                     epilogue(o_, g_)  # e.g. the NCCL gradient exchange: communicators must exist before capture
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -218,7 +383,8 @@ class HotPath:
             join = None
             for dst, src in (uploads or []):
                 dst.copy_(src, non_blocking=True)
-            late = [(d, h) for d, h in ((dL_dimage, dL_host), (target, target_host)) if h is not None]
+            late = [(d, h) for d, h in list(zip(dLs, dL_hosts)) + list(zip(targets or [], target_hosts))
+                    if h is not None]
             if late:
                 main = torch.cuda.current_stream(self.device)
                 up = torch.cuda.Stream(self.device)
@@ -227,22 +393,44 @@ class HotPath:
                     for d, h in late:
                         d.copy_(h, non_blocking=True)
                 join = lambda: main.wait_stream(up)  # noqa: E731
-            out, grads = self.step_grads(view, dL_dimage, compact_sp_W, before_backward=join, **kw)
+            out, grads = run(before_backward=join)
             if epilogue is not None:
                 epilogue(out, grads)
         self.launches_per_step = _lib.launch_count() - n0  # kernels of libskgs_b200.so inside one replay
         torch.cuda.synchronize(self.device)
-        out['_header_words'] = words
-        out['_capacity'] = kw['fixed_capacity']
-        if not hasattr(self, '_graph_words'):
-            self._graph_words = []
-        self._graph_words.append(words)
+        out['_header_words'] = words if multi else words[0]
+        out['_capacity'] = caps if multi else caps[0]
+        self._graph_words.extend(words)
         return graph, out, grads
+
+    def capture_render(self, view: int, headroom: float = 1.3):
+        """Forward only (FK + LBS + assembly + rasterize) of one view as a CUDA graph: the reference's FPS protocol
+        (test.py:102-123) without the host in the loop.  Returns (graph, outputs)."""
+        from . import diff_gaussian_rasterization as DGR
+        cap = self.measure_capacity(view, headroom)
+        words = DGR.new_header_words()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward_raw(view, cap, words)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            out, _ = self.forward_raw(view, cap, words)
+        self.launches_per_render = _lib.launch_count() - n0
+        torch.cuda.synchronize(self.device)
+        out['_header_words'] = words
+        out['_capacity'] = cap
+        self._graph_words.append(words)
+        return graph, out
 
     def overflowed(self) -> bool:
         """True if the most recent (completed) replay of ANY graph captured from this HotPath exceeded its binning
         capacity: that replay's image and gradients are invalid.  Call after a synchronisation point."""
-        return any(int(w[3]) != 0 for w in getattr(self, '_graph_words', []))
+        return any(int(w[3]) != 0 for w in self._graph_words)
 
     def zero_grad(self):
         for t in list(self.params.values()) + [self.sp_radius, self.sp_weight]:

@@ -60,9 +60,9 @@ def test_errors_are_reported_not_swallowed():
     # NULL settings / skeleton are rejected before any CUDA call
     assert L.skgs_raster_forward_geometry(None, 0, 0, *([None] * 10), 0, *([None] * 3)) == -1
     assert b'settings is NULL' in L.skgs_last_error()
-    assert L.skgs_fk_lbs_forward(None, 0, *([None] * 8)) == -1
+    assert L.skgs_fk_lbs_forward(None, 0, *([None] * 9)) == -1
     sk = _lib.Skeleton(M=2000, L=1, root=0, K=5, mode=0, temperature=1.0)
-    assert L.skgs_fk_lbs_forward(C.byref(sk), 0, *([None] * 8)) == -1
+    assert L.skgs_fk_lbs_forward(C.byref(sk), 0, *([None] * 9)) == -1
     assert b'M=2000' in L.skgs_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(-1, 'demo')
@@ -154,6 +154,6 @@ def test_sass_carries_the_instructions_the_design_relies_on():
     assert 'REDG.E.ADD.F64' in sass                                       # image_loss.cu loss sums
     funcs = set(re.findall(r'Function : (\S+)', sass))
     for name in ('composite_fwd_kernel', 'composite_bwd_kernel', 'onesweep_pass_kernel', 'preprocess_scan_kernel',
-                 'fk_lbs_fwd_kernel', 'lbs_bwd_jm_kernel', 'multimem_allreduce_kernel', 'ssim_stats_kernel',
+                 'lbs_fwd_kernel', 'fk_table_kernel', 'lbs_bwd_jm_kernel', 'multimem_allreduce_kernel', 'ssim_stats_kernel',
                  'ssim_grad_kernel', 'adam_kernel', 'small_gemm_kernel'):
         assert any(name in f for f in funcs), name

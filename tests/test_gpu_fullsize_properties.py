@@ -109,6 +109,14 @@ def test_b2_entry_points_match_b1():
                                           net['rotations'], None, net['sh_features'], n, radii, opacity, dC,
                                           torch.zeros_like(opacity), None, None, None, None, geom, binning, img)
     assert out[3].shape == (5000, 3) and bool(torch.isfinite(out[5]).all()) and float(out[5].abs().max()) > 0
+    # the state travels in three plain uint8 tensors, like the reference's geomBuffer / binningBuffer / imgBuffer
+    assert all(t.dtype == torch.uint8 and t.is_cuda for t in (geom, binning, img))
+    _, _, _, _, st0 = DGR.rasterize_forward(rs._replace(bg=None), net['points'], net['opacity'], shs=net['sh_features'],
+                                            scales=net['scales'], rotations=net['rotations'], quat_wxyz=False)
+    gb1 = DGR.rasterize_backward(st0, dC, None, torch.zeros(1, *opacity.shape, device='cuda'))  # B2 has no background
+    for got, want in ((out[0], gb1['means2D']), (out[2], gb1['opacities']), (out[3], gb1['means3D']),
+                      (out[5], gb1['shs']), (out[6], gb1['scales']), (out[7], gb1['rotations'])):
+        assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
     with pytest.raises(RuntimeError):
         rasterize_gaussians_b2(rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, 3, 1.0, False, False, True,
                                rs.viewmatrix, rs.projmatrix, rs.campos, net['points'], net['opacity'],

@@ -9,7 +9,7 @@ import torch
 from sk_gs_b200 import scene as S, _lib
 from sk_gs_b200.pipeline import HotPath
 cfg = S.CONFIGS[%r]
-hp = HotPath(S.make_scene(cfg, views=1), 'cuda:0')
+hp = HotPath(S.make_scene(cfg, views=1), 'cuda:0', merged_sh=True, requires_grad=False)
 dL = (torch.randn(3, cfg.H, cfg.W) / (3 * cfg.H * cfg.W)).cuda()
 for _ in range(3): hp.step_grads(0, dL)
 torch.cuda.synchronize()
@@ -24,9 +24,14 @@ a.record()
 for _ in range(100): g.replay()
 b.record(); torch.cuda.synchronize()
 sort = sum(v[1] for k, v in pr.items() if k.startswith('onesweep')) / 5
-print('%%-10s graph %%.1f us | comp_fwd %%.1f comp_bwd %%.1f sort %%.1f' %% (os.environ.get('VNAME'), a.elapsed_time(b) * 10, pr['composite_fwd_kernel'][1] / 5, pr['composite_bwd_kernel'][1] / 5, sort))
+print('%%-22s pdl=%%s graph %%.1f us | pre %%.1f sort %%.1f order %%.1f comp_fwd %%.1f comp_bwd %%.1f pre_bwd %%.1f' %% (os.environ.get('VNAME'), os.environ.get('SKGS_PDL', '1'), a.elapsed_time(b) * 10, pr['preprocess_scan_kernel'][1] / 5, sort, pr['tile_order_kernel'][1] / 5, pr['composite_fwd_kernel'][1] / 5, pr['composite_bwd_kernel'][1] / 5, pr['preprocess_bwd_kernel'][1] / 5))
 ''' % (ROOT, wl)
-for lib in sorted(glob.glob(os.path.join(ROOT, 'sk_gs_b200', 'variants', 'libskgs_*.so'))):
-    env = dict(os.environ, SKGS_LIB=lib, VNAME=os.path.basename(lib)[8:-3])
+libs = {os.path.basename(l)[8:-3]: l for l in sorted(glob.glob(os.path.join(ROOT, 'sk_gs_b200', 'variants', 'libskgs_*.so')))}
+runs = [(n, {}) for n in libs]
+runs += [('base', {'SKGS_PDL': '0'})]
+runs += [('base', {'SKGS_FWD_CTAS': str(f)}) for f in (3, 4, 5, 6)]
+runs += [('base', {'SKGS_BWD_CTAS': str(b)}) for b in (2, 3, 4)]
+for name, extra in runs:
+    env = dict(os.environ, SKGS_LIB=libs[name], VNAME=name + ''.join(f' {k[5:]}={v}' for k, v in extra.items()), **extra)
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr.strip().splitlines()[-1], flush=True)

@@ -5,18 +5,9 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 VARIANTS = {
     'base': [],
-    'warps2': ['-DSKGS_CW_WARPS=2'],
-    'bwdmin6': ['-DSKGS_BWD_MINBLOCKS=6'],
-    'rslots7': ['-DSKGS_RSLOTS=7'],
-    'rslots4': ['-DSKGS_RSLOTS=4'],
-    'os8': ['-DSKGS_OS_ITEMS=8'],
-    'os24': ['-DSKGS_OS_ITEMS=24'],
-    'gw8j1': ['-DSKGS_GM_WARPS=8', '-DSKGS_GM_JW=1'],
-    'gw8j2': ['-DSKGS_GM_WARPS=8', '-DSKGS_GM_JW=2'],
-    'gw4j1': ['-DSKGS_GM_WARPS=4', '-DSKGS_GM_JW=1'],
-    'adilp4': ['-DSKGS_AD_ILP=4', '-DSKGS_AD_MINB=2'],
-    'adilp1': ['-DSKGS_AD_ILP=1', '-DSKGS_AD_MINB=8'],
-    'adilp2b8': ['-DSKGS_AD_ILP=2', '-DSKGS_AD_MINB=6'],
+    'os12': ['-DSKGS_OS_ITEMS=12'],
+    'os32': ['-DSKGS_OS_ITEMS=32'],
+    'os48': ['-DSKGS_OS_ITEMS=48'],
 }
 out_dir = os.path.join(ROOT, 'sk_gs_b200', 'variants')
 os.makedirs(out_dir, exist_ok=True)
