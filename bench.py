@@ -185,8 +185,12 @@ class Runner:
         multi_view = len(self.my_views) > 1
         if world > 1:
             self.arena = (GradArena if args.allreduce == 'nccl' else SymmGradArena)(shapes, dev, order=list(shapes))
-            self.exchange_kind = 'NVLS multimem all-reduce kernel (symmetric memory)' \
-                if getattr(self.arena, 'multimem', False) else 'NCCL all-reduce'
+            if getattr(self.arena, 'multimem', False):
+                self.exchange_kind = 'NVLS multimem all-reduce kernel over symmetric memory' + \
+                    (', both cross-GPU barriers inside the launch' if getattr(self.arena, 'synced', False)
+                     and args.exchange == 'synced' else ' between two signal-pad barrier kernels')
+            else:
+                self.exchange_kind = 'NCCL all-reduce'
         elif multi_view:
             self.arena = GradArena(shapes, dev, order=list(shapes))
         if multi_view:
@@ -205,9 +209,15 @@ class Runner:
             return
         a = self.arena
         if self.split_exchange:  # the rasterizer-side blocks were reduced under the LBS / FK backward (mid_backward)
-            a.allreduce_range(a.block_start('sp_W'), a.flat_padded.numel(), channel=1)
+            if self.args.exchange == 'synced':   # one launch: barrier + reduce + barrier (covers the first range too)
+                a.allreduce_range_synced(a.block_start('sp_W'), a.flat_padded.numel(), slot=1, exit_barrier=True)
+            else:
+                a.allreduce_range(a.block_start('sp_W'), a.flat_padded.numel(), channel=1)
         else:
-            a.allreduce(chunks=1)
+            if getattr(a, 'synced', False) and self.args.exchange == 'synced':
+                a.allreduce_range_synced(0, a.flat_padded.numel(), slot=0)
+            else:
+                a.allreduce(chunks=1)
             self._allreduce_max(out['radii'])
 
     def after_forward(self, radii):
@@ -224,7 +234,12 @@ class Runner:
         main = torch.cuda.current_stream(self.dev)
         self.side2.wait_stream(main)
         with torch.cuda.stream(self.side2):
-            self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0)
+            if self.args.exchange == 'synced':
+                # no exit barrier: every rank's second range (exchange(), after the join below) starts behind it
+                self.arena.allreduce_range_synced(0, self.arena.block_start('sp_W'), slot=0, exit_barrier=False,
+                                                  max_blocks=self.args.mm_blocks)
+            else:
+                self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0)
         return lambda: main.wait_stream(self.side2)
 
     def capture(self, e2e: bool):
@@ -307,13 +322,24 @@ class Runner:
         torch.cuda.synchronize()
         got = self.arena.flat[:ref.numel()]
         err = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        worst, bad = None, {}  # the block of the arena with the largest deviation (diagnostic)
+        for name in self.shapes:
+            b0 = self.arena.block_start(name)
+            n = 1
+            for d_ in self.shapes[name]:
+                n *= d_
+            e_ = float((got[b0:b0 + n] - ref[b0:b0 + n]).abs().max() / ref[b0:b0 + n].abs().max().clamp_min(1e-30))
+            if e_ > 1e-5:
+                bad[name] = e_
+            if worst is None or e_ > worst[1]:
+                worst = (name, e_)
         radii_ok = True
         if self.graphs.get('dev') is not None:
             radii_ok = bool(torch.equal(self.graphs['dev'][1]['radii'], radii))
         t = torch.tensor([err, 0.0 if radii_ok else 1.0], device=self.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return {'max_rel_err_vs_nccl_allreduce': float(t[0]), 'radii_max_equal': bool(t[1] == 0),
-                'ok': bool(t[0] <= 1e-5 and t[1] == 0), 'what': 'arena after the in-graph exchange vs '
+                'ok': bool(t[0] <= 1e-5 and t[1] == 0), 'worst_block_rank0': list(worst), 'bad_blocks_rank0': bad, 'what': 'arena after the in-graph exchange vs '
                 'dist.all_reduce(SUM) of the same per-rank gradients; fp32 sums in a different order'}
 
 
@@ -896,6 +922,10 @@ def main():
     ap.add_argument('--no-iteration', action='store_true', help='skip the MLP+loss+Adam full-iteration section')
     ap.add_argument('--no-workloads', action='store_true', help='skip the ns / c3 / c4 / c5 section')
     ap.add_argument('--headline-only', action='store_true', help='only value / e2e / kernels (quick runs)')
+    ap.add_argument('--exchange', default='synced', choices=['synced', 'barriers'],
+                    help='multimem exchange: one launch with both cross-GPU barriers inside (synced), or the bare '
+                         'kernel between two symmetric-memory barrier kernels')
+    ap.add_argument('--mm-blocks', type=int, default=0, help='grid cap of the overlapped all-reduce (0: default)')
     ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
                     help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
     args = ap.parse_args()

@@ -373,6 +373,19 @@ SKGS_API int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_
  * same stream.  The reference has no counterpart (its DDP wiring is unused, my_ext/framework.py:339-357). */
 SKGS_API int skgs_multimem_allreduce(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world, void* stream);
 
+/* The same all-reduce with BOTH cross-GPU barriers inside the one launch (fused compute + synchronisation over NVLink
+ * peer memory): block 0 exchanges an epoch flag with every peer through the symmetric-memory signal pads
+ * (`signal_pads_dev`: device array of `world` pointers, one pad per rank, e.g. handle.signal_pad_ptrs_dev; the kernel
+ * uses the 2 * world uint32 words [channel * world, (channel + 2) * world) of every pad) before any block reduces, and
+ * the last block to finish does the same after its stores are fenced - unless `exit_barrier` == 0, for a range whose
+ * completion is covered by a later synced call on the same stream of every rank.
+ * `ctrl`: 16 bytes of zero-initialised device memory private to this (arena, channel) pair; it carries the epoch, so a
+ * captured CUDA graph can be replayed.  ctrl[3] != 0 afterwards means a peer never arrived (result invalid, no hang).
+ * `max_blocks` (> 0) caps the grid, e.g. for a call that overlaps other kernels. */
+SKGS_API int skgs_multimem_allreduce_synced(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world,
+                                            void* const* signal_pads_dev, int32_t channel, void* ctrl,
+                                            int32_t exit_barrier, int32_t max_blocks, void* stream);
+
 /* Multi-view steps: the reference loops over the views of a step and autograd SUMS their gradients
  * (networks/sk_gs.py:1220); the MAX of the screen radii over the views feeds max-radius tracking
  * (networks/gaussian_splatting.py:638-640).  dst[i] += src[i] over a flat fp32 arena (both 16-byte aligned) and

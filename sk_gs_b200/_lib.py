@@ -106,6 +106,7 @@ _SIGNATURES = {
     'skgs_joint_mlp_forward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_joint_mlp_backward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
+    'skgs_multimem_allreduce_synced': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
     'skgs_accumulate_f32': (C.c_int, [_vp, _vp, _i64, _vp]),
     'skgs_max_i32': (C.c_int, [_vp, _vp, _i64, _vp]),
 }

@@ -506,8 +506,11 @@ struct DeformIO {
   int64_t* indices;
 };
 
+#ifndef SKGS_DP_MINBLOCKS
+#define SKGS_DP_MINBLOCKS 3   // 3 CTAs x 256 threads per SM: the whole grid of c2 is resident at once (A/B: -15 us)
+#endif
 template <int KT>
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, SKGS_DP_MINBLOCKS)
 deform_preprocess_kernel(RasterParams rp, DeformIO io, const float* __restrict__ shs, GeomOut go,
                          uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ point_offsets,
                          uint64_t* __restrict__ scan_state, float4* __restrict__ ggrad,
@@ -633,31 +636,61 @@ duplicate_keys_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, 
 //     ranges[tile] (identifyTileRanges of the reference, gaussian_rasterizer_forward.cu:77-94, without a kernel).
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef SKGS_OS_THREADS
-#define SKGS_OS_THREADS 256
+#define SKGS_OS_THREADS 512
 #endif
 #ifndef SKGS_OS_ITEMS
-#define SKGS_OS_ITEMS 24   // 6144 keys per CTA tile: fewer, longer tiles beat more CTAs (shorter look-back chains)
+#define SKGS_OS_ITEMS 12   // 512 x 12 = 6144 keys per CTA tile, 16 warps: every phase is latency bound, warps hide it
 #endif
 constexpr int OS_THREADS = SKGS_OS_THREADS;
 constexpr int OS_ITEMS = SKGS_OS_ITEMS;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // keys per CTA tile
 constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_DIGITS = 256;                  // threads 0..255 also own one digit each
+constexpr int OS_DWARPS = OS_DIGITS / 32;
 constexpr uint32_t OS_FLAG_AGG = 1u, OS_FLAG_INC = 2u;
 constexpr uint32_t OS_VAL_MASK = (1u << 27) - 1;
-static_assert(OS_THREADS == 256, "one thread per digit");
+static_assert(OS_THREADS >= OS_DIGITS && OS_THREADS % 32 == 0, "one thread per digit");
 static_assert(OS_TILE >= 2048, "api.cu sizes the look-back words for tiles of at least 2048 keys");
-static_assert(OS_TILE * 12 >= OS_WARPS * 32 * 33 * 4, "the look-back slabs alias the key + value staging area");
+static_assert(OS_TILE * 12 >= OS_DWARPS * 32 * 33 * 4, "the look-back slabs alias the key + value staging area");
+
+// debug: per-tile phase timestamps of one radix pass (tools/sort_trace.py)
+__device__ unsigned long long* g_os_trace = nullptr;
+__device__ __forceinline__ void os_trace(uint32_t tile, int phase) {
+  if (g_os_trace != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_os_trace[(size_t)tile * 8 + phase] = t;
+  }
+}
 
 struct OnesweepSmem {
-  uint64_t keys[OS_TILE];   // reorder staging; during the look-back keys + vals hold OS_WARPS slabs of 32 x 33 words
+  uint64_t keys[OS_TILE];   // reorder staging; during the look-back keys + vals hold OS_DWARPS slabs of 32 x 33 words
   uint32_t vals[OS_TILE];
-  uint32_t whist[OS_WARPS][256];
-  uint32_t texcl[256];   // exclusive prefix of this tile's digit counts
-  uint32_t goff[256];    // global output offset of digit d minus texcl[d]
-  uint32_t gbase[256];   // exclusive prefix of the global digit histogram
-  uint32_t warp_tot[OS_WARPS];
+  uint32_t whist[OS_WARPS][OS_DIGITS];
+  uint32_t texcl[OS_DIGITS];   // exclusive prefix of this tile's digit counts
+  uint32_t goff[OS_DIGITS];    // global output offset of digit d minus texcl[d]
+  uint32_t gbase[OS_DIGITS];   // exclusive prefix of the global digit histogram
+  uint32_t warp_tot[OS_DWARPS];
   uint32_t tile;
 };
+
+// exclusive scan over the 256 digits, one value per thread of the first 8 warps (all threads must call: barriers)
+__device__ __forceinline__ uint32_t digit_exclusive_scan(uint32_t v, int tid, uint32_t* warp_tot) {
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (tid < OS_DIGITS && lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  if (tid < OS_DIGITS)
+    for (int w = 0; w < warp; w++) woff += warp_tot[w];
+  __syncthreads();
+  return woff + incl - v;
+}
 
 __global__ void __launch_bounds__(OS_THREADS)
 onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint64_t* __restrict__ keys_b,
@@ -667,6 +700,7 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   OnesweepSmem& S = *reinterpret_cast<OnesweepSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool dthread = tid < OS_DIGITS;  // owns digit `tid`
   pdl_wait();
   pdl_trigger();
   if (hdr->overflow) return;
@@ -684,21 +718,11 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
   const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
-  // exclusive scan of the global digit histogram (256 values, one per thread)
+  // exclusive scan of the global digit histogram
   {
-    const uint32_t c = hist[tid];
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) S.warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; w++) woff += S.warp_tot[w];
-    S.gbase[tid] = woff + incl - c;
-    __syncthreads();
+    const uint32_t c = dthread ? hist[tid] : 0u;
+    const uint32_t ex = digit_exclusive_scan(c, tid, S.warp_tot);
+    if (dthread) S.gbase[tid] = ex;
   }
 
   while (true) {
@@ -708,6 +732,7 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
     if (tile >= num_tiles) break;
     const uint32_t base = tile * OS_TILE;
     const uint32_t cnt = min((uint32_t)OS_TILE, n - base);
+    os_trace(tile, 0);
 
     uint64_t key[OS_ITEMS];
     uint32_t val[OS_ITEMS];
@@ -722,8 +747,9 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
       const uint32_t idx = warp * (32 * OS_ITEMS) + i * 32 + lane;
       val[i] = idx < cnt ? vin[base + idx] : 0u;
     }
-    for (int k = tid; k < OS_WARPS * 256; k += OS_THREADS) (&S.whist[0][0])[k] = 0;
+    for (int k = tid; k < OS_WARPS * OS_DIGITS; k += OS_THREADS) (&S.whist[0][0])[k] = 0;
     __syncthreads();
+    os_trace(tile, 1);
     // ---- stable per-warp ranking (items are warp-striped: item-major, then lane)
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; i++) {
@@ -742,33 +768,28 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
       __syncwarp();
     }
     __syncthreads();
+    os_trace(tile, 2);
     // ---- per digit: cross-warp exclusive prefix, tile totals, publish, look back
     uint32_t total = 0;
     const int d = tid;
+    uint32_t* my = status + (size_t)tile * OS_DIGITS + (dthread ? d : 0);
+    if (dthread) {
 #pragma unroll
-    for (int w = 0; w < OS_WARPS; w++) {
-      const uint32_t c = S.whist[w][d];
-      S.whist[w][d] = total;
-      total += c;
-    }
-    uint32_t* my = status + (size_t)tile * 256 + d;
-    st_volatile_u32(my, (tag << 29) | ((tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG) << 27) | total);
-    {  // exclusive scan of totals over digits
-      uint32_t incl = total;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
+      for (int w = 0; w < OS_WARPS; w++) {
+        const uint32_t c = S.whist[w][d];
+        S.whist[w][d] = total;
+        total += c;
       }
-      if (lane == 31) S.warp_tot[warp] = incl;
-      __syncthreads();
-      uint32_t woff = 0;
-      for (int w = 0; w < warp; w++) woff += S.warp_tot[w];
-      S.texcl[d] = woff + incl - total;
+      st_volatile_u32(my, (tag << 29) | ((tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG) << 27) | total);
     }
+    {  // exclusive scan of totals over digits
+      const uint32_t ex = digit_exclusive_scan(total, tid, S.warp_tot);
+      if (dthread) S.texcl[d] = ex;
+    }
+    os_trace(tile, 3);
     uint32_t excl = 0;
-    if (tile > 0) {
-      // warp-parallel look-back: this warp's digits are 32*warp .. 32*warp+31 (thread tid owns digit tid)
+    if (tile > 0 && dthread) {
+      // warp-parallel look-back: warp w (< 8) owns digits 32w .. 32w+31 (thread tid owns digit tid)
       uint32_t* slab = reinterpret_cast<uint32_t*>(S.keys) + warp * (32 * 33);
       const uint32_t sentinel = (tag << 29) | (OS_FLAG_INC << 27);  // "before tile 0": inclusive prefix 0
       bool done = false;
@@ -777,7 +798,7 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
         const int jj = j0 - lane;
         uint32_t w[32];
         if (jj >= 0) {
-          const uint4* row = reinterpret_cast<const uint4*>(status + (size_t)jj * 256 + warp * 32);
+          const uint4* row = reinterpret_cast<const uint4*>(status + (size_t)jj * OS_DIGITS + warp * 32);
           bool ready;
           do {
             ready = true;
@@ -797,15 +818,15 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
 #pragma unroll
         for (int k = 0; k < 32; k++) slab[lane * 33 + k] = w[k];
         __syncwarp();
-        if (!done) {
-          for (int l = 0; l < 32; l++) {  // predecessors tile-1-j.. in walking order
+        {  // lane k walks the 32 predecessors of its digit in order, branch-free: every read is in flight at once
+          uint32_t alive = done ? 0u : 1u;
+#pragma unroll
+          for (int l = 0; l < 32; l++) {
             const uint32_t x = slab[l * 33 + lane];
-            excl += x & OS_VAL_MASK;
-            if (((x >> 27) & 3u) == OS_FLAG_INC) {
-              done = true;
-              break;
-            }
+            excl += alive ? (x & OS_VAL_MASK) : 0u;
+            alive &= (((x >> 27) & 3u) == OS_FLAG_INC) ? 0u : 1u;
           }
+          done = alive == 0u;
         }
         __syncwarp();
         if (__all_sync(FULL, done)) break;
@@ -813,8 +834,9 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
       }
       st_volatile_u32(my, (tag << 29) | (OS_FLAG_INC << 27) | (excl + total));
     }
-    S.goff[d] = S.gbase[d] + excl - S.texcl[d];
+    if (dthread) S.goff[d] = S.gbase[d] + excl - S.texcl[d];
     __syncthreads();  // look-back slabs (aliasing S.keys) are dead from here on
+    os_trace(tile, 4);
     // ---- reorder through shared memory, then coalesced scatter
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; i++) {
@@ -827,20 +849,32 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_
       }
     }
     __syncthreads();
-    for (uint32_t k = tid; k < cnt; k += OS_THREADS) {
-      const uint64_t kk = S.keys[k];
-      const uint32_t dd = (uint32_t)((kk >> shift) & 255ull);
-      const uint32_t o = S.goff[dd] + k;
-      kout[o] = kk;
-      vout[o] = S.vals[k];
-      if (is_last) {
-        // inside one digit run of this CTA the keys are fully sorted and land on consecutive output slots
-        const uint32_t t = (uint32_t)(kk >> 32);
-        if (k == 0 || (uint32_t)(S.keys[k - 1] >> 32) != t) atomicMin(&ranges[t].x, o);
-        if (k + 1 == cnt || (uint32_t)(S.keys[k + 1] >> 32) != t) atomicMax(&ranges[t].y, o + 1u);
+    // fixed trip count: the shared-memory reads of all of a thread's keys are in flight together
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; i++) {
+      const uint32_t k = tid + i * OS_THREADS;
+      key[i] = k < cnt ? S.keys[k] : 0ull;
+      val[i] = k < cnt ? S.vals[k] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; i++) {
+      const uint32_t k = tid + i * OS_THREADS;
+      if (k < cnt) {
+        const uint64_t kk = key[i];
+        const uint32_t dd = (uint32_t)((kk >> shift) & 255ull);
+        const uint32_t o = S.goff[dd] + k;
+        kout[o] = kk;
+        vout[o] = val[i];
+        if (is_last) {
+          // inside one digit run of this CTA the keys are fully sorted and land on consecutive output slots
+          const uint32_t t = (uint32_t)(kk >> 32);
+          if (k == 0 || (uint32_t)(S.keys[k - 1] >> 32) != t) atomicMin(&ranges[t].x, o);
+          if (k + 1 == cnt || (uint32_t)(S.keys[k + 1] >> 32) != t) atomicMax(&ranges[t].y, o + 1u);
+        }
       }
     }
     __syncthreads();
+    os_trace(tile, 5);
   }
 }
 
@@ -1038,3 +1072,8 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
 }
 
 }  // namespace skgs
+
+extern "C" __attribute__((visibility("default"))) void skgs_debug_set_sort_trace(void* p) {
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+  cudaMemcpyToSymbol(skgs::g_os_trace, &q, sizeof(q));
+}

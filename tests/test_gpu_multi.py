@@ -17,4 +17,4 @@ def test_multimem_allreduce_matches_nccl_world2():
            '127.0.0.1', '--master-port', '29561', os.path.join(ROOT, 'tools', 'mm_test.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert 'split exchange max err' in r.stdout
+    assert 'split exchange max err' in r.stdout and 'synced split exchange max err' in r.stdout

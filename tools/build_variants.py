@@ -5,9 +5,11 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 VARIANTS = {
     'base': [],
-    'os12': ['-DSKGS_OS_ITEMS=12'],
-    'os32': ['-DSKGS_OS_ITEMS=32'],
-    'os48': ['-DSKGS_OS_ITEMS=48'],
+    't256i24': ['-DSKGS_OS_THREADS=256', '-DSKGS_OS_ITEMS=24'],
+    't512i8': ['-DSKGS_OS_ITEMS=8'],
+    't512i16': ['-DSKGS_OS_ITEMS=16'],
+    't1024i6': ['-DSKGS_OS_THREADS=1024', '-DSKGS_OS_ITEMS=6'],
+    't1024i8': ['-DSKGS_OS_THREADS=1024', '-DSKGS_OS_ITEMS=8'],
 }
 out_dir = os.path.join(ROOT, 'sk_gs_b200', 'variants')
 os.makedirs(out_dir, exist_ok=True)
