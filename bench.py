@@ -488,6 +488,11 @@ def run_ours(args, world, rank, local):
             line['full_iteration'] = full_iteration(args, sc, cfg, dev, 0, flush, kern)
         except Exception as e:  # noqa
             line['full_iteration'] = {'error': f'{type(e).__name__}: {e}'[:300]}
+    if rank == 0 and world == 1 and extra_ok and not args.no_workloads:
+        try:
+            line['widening'] = widening_rows(dev, 'ours', flush)
+        except Exception as e:  # noqa
+            line['widening'] = {'error': f'{type(e).__name__}: {e}'[:300]}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -692,6 +697,96 @@ def full_iteration(args, sc, cfg, dev, view, flush, kern):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def widening_rows(dev, impl: str, flush=None):
+    """SURVEY 8 rows f-4 (sp-stage LBS at the default 512 superpoints) and f-3 (densification bookkeeping) at the
+    headline Gaussian count, eager calls, CUDA-event timed.  impl 'ours': libskgs_b200.so through sk_gs_b200.sp_lbs /
+    sk_gs_b200.densify; impl 'reference': the torch op sequences the reference executes for the same functions
+    (networks/sk_gs.py:751-828, networks/gaussian_splatting.py:589-660) as restated in oracle/ - lietorch / pytorch3d
+    are not installable, so this is kind "port" (its rigid action and KNN are plain torch ops)."""
+    P, M, K = 100_000, 512, 5
+    g = torch.Generator().manual_seed(7)
+    r = lambda *s, scale=1.0, shift=0.0: (torch.randn(*s, generator=g) * scale + shift).to(dev)  # noqa: E731
+    points, sp_points, sp_t = r(P, 3, scale=0.5), r(M, 3, scale=0.5), r(M, 3, scale=0.05)
+    sp_r = torch.nn.functional.normalize(r(M, 4, scale=0.2) + torch.tensor([0, 0, 0, 1.0], device=dev), dim=-1)
+    sp_rot = torch.nn.functional.normalize(r(M, 4, scale=0.2) + torch.tensor([0, 0, 0, 1.0], device=dev), dim=-1)
+    sp_scale, sp_W = r(M, 3, scale=0.01), r(P, M)
+    cots = [r(P, 3), r(P, 4), r(P, 3)]
+    out = {}
+    if impl == 'ours':
+        from sk_gs_b200.sp_lbs import sp_warp_backward_raw, sp_warp_forward_raw
+        keep = {}
+
+        def fwd():
+            keep['o'], keep['c'] = sp_warp_forward_raw(points, sp_points, sp_t, sp_r, sp_rot, sp_scale, K=K, mode='W',
+                                                       sp_W=sp_W, method='LBS')
+
+        def bwd():
+            sp_warp_backward_raw(keep['c'], *cots, compact_sp_W=True)
+    else:
+        from oracle import fk_lbs as OF
+        leaves = [t.clone().requires_grad_() for t in (sp_points, sp_t, sp_r, sp_rot, sp_scale, sp_W)]
+        keep = {}
+
+        def fwd():
+            keep['o'] = OF.sp_stage(points, leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], K=K, mode='W',
+                                    sp_W=leaves[5], method='LBS')
+
+        def bwd():
+            o = keep['o']
+            torch.autograd.grad(sum((a * c).sum() for a, c in zip(o[:3], cots)), leaves, allow_unused=True)
+    reps = 20 if impl == 'ours' else 3
+    for _ in range(2):
+        fwd(); bwd()
+    torch.cuda.synchronize()
+    t_f = cuda_time_ms(fwd, reps, flush) / reps
+    fwd()
+    t_fb = cuda_time_ms(lambda: (fwd(), bwd()), reps, flush) / reps
+    out['sp_stage'] = {'what': f'sp-stage LBS forward + backward, P={P} Gaussians, M={M} superpoints, K={K}, mode W, '
+                               f'method LBS, sep_rot', 'forward_us': round(t_f * 1e3, 1),
+                       'forward_backward_us': round(t_fb * 1e3, 1)}
+    # ---- densification: clone + split + prune of the whole per-Gaussian state (6 tensors + 2 Adam moments each)
+    params = dict(xyz=r(P, 3, scale=0.5), shs=r(P, 16, 3), scaling=r(P, 3, shift=-3.6), rotation=r(P, 4),
+                  opacity=r(P, 1, scale=3.0, shift=-2.0), sp_W=r(P, 32))
+    trip = {n: (p, torch.zeros_like(p), torch.zeros_like(p)) for n, p in params.items()}
+    accum = (torch.rand(P, generator=g) * 1.2e-3).to(dev)
+    denom = torch.randint(0, 4, (P,), generator=g).float().to(dev)
+    radii = torch.randint(0, 40, (P,), generator=g).float().to(dev)
+    noise = r(2 * P, 3)
+    kw = dict(do_densify=True, do_prune=True, grad_threshold=0.0002, densify_extent=0.02, min_opacity=0.005,
+              max_screen_size=20.0, prune_extent=0.2)
+    if impl == 'ours':
+        from sk_gs_b200.densify import DensifyStats, add_densification_stats, densify_and_prune
+        st = DensifyStats(P, dev)
+        st.grad_accum, st.denom, st.max_radii2D = accum, denom, radii
+        res = {}
+
+        def dens():
+            res['r'] = densify_and_prune(trip, st, noise=noise, **kw)
+        vs, rad = r(P, 3, scale=1e-4), torch.randint(0, 40, (P,), generator=g).int().to(dev)
+        st2 = DensifyStats(P, dev)
+        t_s = cuda_time_ms(lambda: add_densification_stats(st2, rad, vs), 20, flush) / 20
+        n_new = lambda: res['r'].counts['n_new']  # noqa: E731
+    else:
+        from oracle import densify as OD
+        res = {}
+
+        def dens():
+            res['r'] = OD.densify_and_prune(trip, accum.clone(), denom.clone(), radii.clone(), noise=noise, **kw)
+        vs, rad = r(P, 3, scale=1e-4), torch.randint(0, 40, (P,), generator=g).int().to(dev)
+        a2, d2, m2 = torch.zeros(P, device=dev), torch.zeros(P, device=dev), torch.zeros(P, device=dev)
+        t_s = cuda_time_ms(lambda: OD.add_densification_stats(a2, d2, m2, rad, vs), 5, flush) / 5
+        n_new = lambda: int(res['r'][0]['xyz'][0].shape[0])  # noqa: E731
+    dens()
+    torch.cuda.synchronize()
+    reps = 10 if impl == 'ours' else 3
+    t_d = cuda_time_ms(dens, reps, flush) / reps
+    out['densify'] = {'what': f'clone + split + prune of P={P} Gaussians (6 parameter tensors incl. a 32-column skinning '
+                              f'table, each with both Adam moments) including the host read of the new count',
+                      'P_new': n_new(), 'densify_and_prune_us': round(t_d * 1e3, 1),
+                      'per_step_statistics_us': round(t_s * 1e3, 1)}
+    return out
+
+
 def cpu_baseline(workload: str, steps: int = 2, threads: int = 0):
     """Oracle port (torch FK/LBS + C rasterizer) on the host cores: `steps` full fwd+bwd steps of the same workload."""
     from oracle import raster as OR
@@ -904,6 +999,11 @@ def run_reference(args, world, rank, local):
             wl['c5'] = {'error': f'{type(e).__name__}: {e}'[:300]}
         torch.cuda.empty_cache()
         line['workloads'] = wl
+        if dev.type == 'cuda':
+            try:
+                line['widening'] = widening_rows(dev, 'reference', flush)
+            except Exception as e:  # noqa
+                line['widening'] = {'error': f'{type(e).__name__}: {e}'[:300]}
     print(json.dumps(line), flush=True)
 
 

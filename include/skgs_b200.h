@@ -260,6 +260,53 @@ SKGS_API int skgs_assemble_backward(int32_t P, const float* scaling, const float
                                     float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_xyz,
                                     float* dL_dd_rot, float* dL_dd_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * sp-stage LBS: the superpoint twin of skgs_fk_lbs_*.  Replaces `warp` (networks/sk_gs.py:776-828)
+ * and `calc_LBS_weight` (:751-774) as `sp_stage` calls them (:830-856): the per-superpoint SE3 comes from the
+ * deformation network (sp_t = d_xyz, sp_r = normalize(d_rotation + bias)) instead of from forward kinematics.
+ *   d_points   = sum_k w_k (R(sp_r_k) p + t_k) - p          method LBS   : t = sp_t
+ *                                                           method LBS_C : t = sp_t + c + R(sp_r)(-c), c = sp_points
+ *                R(sp_r_a) p + t_a - p, a = argmax_k w_k     method LARGEST (t as LBS)
+ *   d_rotation = sum_k w_k sp_rot_k   (sp_rot == NULL: sp_r, :818-821);   d_scales = sum_k w_k sp_scale_k (NULL: 0)
+ *   spT [M][7] = (t, sp_r)
+ * Gradients w.r.t. sp_r through the rigid action are the tangent-space-projected ones lietorch's FromVec backward
+ * returns (the component along sp_r is removed); the blend d_rotation = sum w sp_r contributes its plain gradient.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef enum skgs_warp_method { SKGS_WARP_LBS = 0, SKGS_WARP_LBS_C = 1, SKGS_WARP_LARGEST = 2 } skgs_warp_method;
+
+typedef struct skgs_superpoints {
+  int32_t M;               /* superpoints, 1..1024 (exps/default.yaml:25: 512) */
+  int32_t K;               /* nearest superpoints per Gaussian, 1..8 */
+  int32_t mode;            /* skgs_lbs_mode */
+  int32_t method;          /* skgs_warp_method */
+  float temperature;       /* SKGS_LBS_DIST only */
+  const float* sp_points;  /* [M][3] */
+  const float* sp_t;       /* [M][3] */
+  const float* sp_r;       /* [M][4] xyzw (unit; normalised again inside) */
+  const float* sp_rot;     /* [M][4] residual rotation blended into d_rotation, or NULL (blend sp_r) */
+  const float* sp_scale;   /* [M][3] residual scale, or NULL */
+  const float* sp_W;       /* [P][M]   (mode W) */
+  const float* sp_radius;  /* [M] log-radius (kernel modes) */
+  const float* sp_weight;  /* [M] logit (weighted_kernel) */
+} skgs_superpoints;
+
+SKGS_API size_t skgs_sp_lbs_workspace_bytes(int32_t M);
+/* points [P][3] (constant: :834 detaches).  Outputs: d_points [P][3], d_rotation [P][4], d_scales [P][3], spT [M][7]
+ * (may be NULL), weights [P][K], indices int64 [P][K]. */
+SKGS_API int skgs_sp_lbs_forward(const skgs_superpoints* sp, int32_t P, const float* points, float* d_points,
+                                 float* d_rotation, float* d_scales, float* spT, float* weights, int64_t* indices,
+                                 void* workspace, void* stream);
+/* Incoming gradients may be NULL (= zero); dL_dspT [M][7] / dL_dweights [P][K] are direct gradients on the auxiliary
+ * outputs.  Outgoing (NULL = not wanted): dL_dsp_points [M][3] (through the weight function's distances and, LBS_C,
+ * the centred rotation), dL_dsp_t [M][3], dL_dsp_r [M][4], dL_dsp_rot [M][4], dL_dsp_scale [M][3], dL_dsp_W [P][M]
+ * (dense) or dL_dsp_W_knn [P][K] (compact), dL_dsp_radius [M], dL_dsp_weight [M]. */
+SKGS_API int skgs_sp_lbs_backward(const skgs_superpoints* sp, int32_t P, const float* points, const float* spT,
+                                  const float* weights, const int64_t* indices, const float* dL_dd_points,
+                                  const float* dL_dd_rotation, const float* dL_dd_scales, const float* dL_dspT,
+                                  const float* dL_dweights, float* dL_dsp_points, float* dL_dsp_t, float* dL_dsp_r,
+                                  float* dL_dsp_rot, float* dL_dsp_scale, float* dL_dsp_W, float* dL_dsp_W_knn,
+                                  float* dL_dsp_radius, float* dL_dsp_weight, void* workspace, void* stream);
+
 /* The per-Gaussian forward of one view in TWO launches instead of four: forward kinematics once (one CTA), then one
  * kernel that does K nearest joints + skinning weights + linear blend + output assembly + preprocess + prefix sum + key
  * emission.  Same device functions and build flags as skgs_fk_lbs_forward -> skgs_assemble_forward ->
@@ -331,6 +378,78 @@ typedef struct skgs_adam_tensor {
 SKGS_API int skgs_adam_step(const skgs_adam_tensor* tensors /* host */, int32_t count, int32_t step, double beta1,
                             double beta2, double eps, float grad_scale, const float* dynamic_hyper,
                             const uint32_t* skip_if_nonzero, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Densification bookkeeping, networks/gaussian_splatting.py:503-703.
+ *
+ * skgs_densify_stats: the per-step statistics of adaptive_control (:669-675 -> add_densification_stats :503-513):
+ *   for every Gaussian with radii > 0:  max_radii2D = max(max_radii2D, radii);  grad_accum += |viewspace_grad[:2]|;
+ *   denom += 1.   viewspace_grad is [P][grad_stride] (the rasterizer's dL/dmeans2D, stride 3; multi-view steps pass the
+ *   SUM over views and the MAX of the radii, :509-512, :670-671).  `skip_if_nonzero`: as in skgs_adam_step.
+ *
+ * skgs_densify_plan + skgs_densify_apply: densify (:640-645 = clone :624-638 then split :589-622) and / or prune
+ *   (:653-660) in ONE gather instead of four rounds of torch.cat / mask indexing over every parameter and both Adam
+ *   moments (change_optimizer :515-563).  The plan decides per existing Gaussian
+ *     g = grad_accum / denom (NaN -> 0);   hot = g >= grad_threshold;   smax = max exp(scaling)
+ *     clone  = hot && smax <= densify_extent         (densify_percent_dense * cameras_extent)
+ *     split  = hot && smax >  densify_extent         (N = 2 samples, the original is dropped)
+ *     pruned = sigmoid(opacity) < min_opacity || (max_screen_size > 0 && (max_radii2D > max_screen_size ||
+ *              smax > prune_extent))                 evaluated on the element's OWN values: clones inherit them,
+ *              samples carry scaling log(exp(s) / 1.6); max_radii2D counts as 0 when do_densify (the reference zeroes
+ *              it in densification_postfix :586 before prune runs)
+ *   and lays the survivors out in the reference's final order
+ *     [ kept originals | clones | split samples n = 0 | split samples n = 1 ]   (each in index order)
+ *   as src[d] (source Gaussian of slot d), kind[d] (0 kept, 1 clone, 2 / 3 sample n = 0 / 1) and noise_row[d]
+ *   (n * n_selected + rank of the source among the split-selected: the row of `samples` at :601-603).  src / kind /
+ *   noise_row need room for 2 P entries.  `counts` (device) is written by the plan; the host reads it to size the new
+ *   arrays and the noise table ([2 n_selected][3] standard normal: torch.normal(0, std) = noise * std).
+ *   The apply pass gathers every listed tensor (row width `width`) and its Adam moments: kept rows keep their moments,
+ *   new rows start at zero (:548-552); role XYZ rows of samples become R(normalize(rotation)) (noise * exp(scaling)) +
+ *   xyz (:600-610), role SCALING rows of samples log(exp(s) / 1.6) (:611).
+ * skgs_opacity_reset: reset_opacity (:662-665) - opacity = logit(min(sigmoid(opacity), cap)), moments zeroed.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct skgs_densify_config {
+  int32_t do_densify;     /* clone + split */
+  int32_t do_prune;
+  float grad_threshold;   /* densify_grad_threshold (exps/default.yaml:70) */
+  float densify_extent;   /* densify_percent_dense * cameras_extent */
+  float min_opacity;      /* prune_opacity_threshold */
+  float max_screen_size;  /* prune_max_screen_size, <= 0: the two size tests are off (size_threshold None, :688-691) */
+  float prune_extent;     /* prune_percent_dense * cameras_extent */
+} skgs_densify_config;
+
+typedef struct skgs_densify_counts {
+  uint32_t n_keep, n_clone, n_split, n_selected, n_new, reserved[3];
+} skgs_densify_counts;
+
+typedef enum skgs_densify_role { SKGS_DENSIFY_ROLE_COPY = 0, SKGS_DENSIFY_ROLE_XYZ = 1, SKGS_DENSIFY_ROLE_SCALING = 2 }
+    skgs_densify_role;
+
+#define SKGS_DENSIFY_MAX_TENSORS 16
+typedef struct skgs_densify_tensor {
+  const float* in;    /* [P][width] */
+  float* out;         /* [P_new][width] */
+  const float* m_in;  /* Adam exp_avg (or NULL) */
+  float* m_out;
+  const float* v_in;  /* Adam exp_avg_sq (or NULL) */
+  float* v_out;
+  int32_t width;
+  int32_t role;       /* skgs_densify_role */
+} skgs_densify_tensor;
+
+SKGS_API int skgs_densify_stats(int32_t P, const int32_t* radii, const float* viewspace_grad, int32_t grad_stride,
+                                float* max_radii2D, float* grad_accum, float* denom, const uint32_t* skip_if_nonzero,
+                                void* stream);
+SKGS_API size_t skgs_densify_workspace_bytes(int32_t P);
+SKGS_API int skgs_densify_plan(const skgs_densify_config* cfg, int32_t P, const float* scaling, const float* opacity,
+                               const float* grad_accum, const float* denom, const float* max_radii2D, int32_t* src,
+                               uint8_t* kind, int32_t* noise_row, skgs_densify_counts* counts /* device */,
+                               void* workspace, void* stream);
+SKGS_API int skgs_densify_apply(const skgs_densify_tensor* tensors /* host */, int32_t count, int32_t P_new,
+                                const int32_t* src, const uint8_t* kind, const int32_t* noise_row,
+                                const float* scaling /* source [P][3] */, const float* rotation /* source [P][4] xyzw */,
+                                const float* noise /* [2 n_selected][3] */, void* stream);
+SKGS_API int skgs_opacity_reset(int32_t P, float* opacity, float* exp_avg, float* exp_avg_sq, float cap, void* stream);
 
 /* Joint-rotation network of the `sk` stage, the step before forward kinematics:
  * joints [M,3], time t -> sk_r [M,4] (unit quaternion xyzw), d_rot [M,4], d_scale [M,3].

@@ -227,6 +227,45 @@ def sk_stage(xyz: Tensor, joints: Tensor, sk_r: Tensor, sk_d_rot: Tensor, sk_d_s
     return d_xyz, d_rot, d_scale, sk_T, sk_d_rot, sk_d_scale, g_tr, w, idx
 
 
+# -------------------------------------------------------------------------------------------------------- sp_stage
+def sp_warp(points: Tensor, sp_points: Tensor, sp_t: Tensor, sp_r: Tensor, sp_rot: Optional[Tensor],
+            sp_scale: Optional[Tensor], weights: Tensor, indices: Tensor, method: str = 'LBS'):
+    """`warp` (:776-828), tensor branch of sp_t (:794-799), SE3 branch of spT (:807-812).
+
+    lietorch (un-vendored, "parity unpinned" for its internals) supplies SE3.act(p) = R(q) p + t (lie.h:246, q used as
+    is) and returns gradients w.r.t. the 7-vector projected onto the tangent space at (t, q) (FromVec backward: tangent
+    gradient times pinv of the orthogonal projector).  Both are reproduced by evaluating the action with q / |q|: equal
+    values for the unit quaternions `sp_stage` passes (:847), and autograd through the normalisation IS that projection.
+    Pinned on the reference's own `warp` code run with a functional lietorch stand-in: tests/golden/sp_stage.npz."""
+    q = q_normalize(sp_r)
+    t = sp_t
+    if method == 'LBS_c':
+        t = sp_t + sp_points + q_rotate(q, -sp_points)
+    spT = torch.cat([t, q], dim=-1)
+    if method in ('LBS', 'LBS_c'):
+        d_points = (se3_act(spT[indices], points[:, None, :]) * weights[..., None]).sum(dim=1) - points
+    elif method == 'largest':
+        p2sp = torch.gather(indices, -1, weights.argmax(dim=-1, keepdim=True))[:, 0]  # :850-851
+        d_points = se3_act(spT[p2sp], points) - points
+    else:
+        raise ValueError(method)
+    rot = sp_rot if sp_rot is not None else sp_r
+    d_rotation = (rot[indices] * weights[..., None]).sum(dim=1)
+    d_scales = (sp_scale[indices] * weights[..., None]).sum(dim=1) if sp_scale is not None else None
+    return d_points, d_rotation, d_scales, spT
+
+
+def sp_stage(points: Tensor, sp_points: Tensor, sp_t: Tensor, sp_r: Tensor, sp_rot: Optional[Tensor],
+             sp_scale: Optional[Tensor], K: int = 5, mode: str = 'W', sp_W: Optional[Tensor] = None,
+             sp_radius: Optional[Tensor] = None, sp_weight: Optional[Tensor] = None, temperature: float = 1.0,
+             method: str = 'LBS'):
+    """`sp_stage` (:830-856) minus the deformation network: weights (:843) then warp (:852-855).
+    -> (d_points, d_rotation, d_scales, spT, weights, indices)."""
+    points = points.detach()
+    w, idx = lbs_weights(points, sp_points, K, mode, sp_W, sp_radius, sp_weight, temperature)
+    return sp_warp(points, sp_points, sp_t, sp_r, sp_rot, sp_scale, w, idx, method) + (w, idx)
+
+
 def assemble(_xyz: Tensor, _scaling: Tensor, _rotation: Tensor, _opacity: Tensor, f_dc: Tensor, f_rest: Tensor,
              d_xyz: Tensor, d_rot: Tensor, d_scale: Tensor):
     """Output assembly of `forward` (:1162-1163,1192,1202-1203) with the activations of

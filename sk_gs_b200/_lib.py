@@ -49,6 +49,26 @@ class Skeleton(C.Structure):
     ]
 
 
+class Superpoints(C.Structure):
+    """struct skgs_superpoints (sp-stage LBS)."""
+    _fields_ = [
+        ('M', C.c_int32), ('K', C.c_int32), ('mode', C.c_int32), ('method', C.c_int32), ('temperature', C.c_float),
+        ('sp_points', C.c_void_p), ('sp_t', C.c_void_p), ('sp_r', C.c_void_p), ('sp_rot', C.c_void_p),
+        ('sp_scale', C.c_void_p), ('sp_W', C.c_void_p), ('sp_radius', C.c_void_p), ('sp_weight', C.c_void_p),
+    ]
+
+
+class DensifyConfig(C.Structure):
+    _fields_ = [('do_densify', C.c_int32), ('do_prune', C.c_int32), ('grad_threshold', C.c_float),
+                ('densify_extent', C.c_float), ('min_opacity', C.c_float), ('max_screen_size', C.c_float),
+                ('prune_extent', C.c_float)]
+
+
+class DensifyTensor(C.Structure):
+    _fields_ = [('in_', C.c_void_p), ('out', C.c_void_p), ('m_in', C.c_void_p), ('m_out', C.c_void_p),
+                ('v_in', C.c_void_p), ('v_out', C.c_void_p), ('width', C.c_int32), ('role', C.c_int32)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [
         ('param', C.c_void_p), ('grad', C.c_void_p), ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p),
@@ -67,6 +87,7 @@ class JointMlp(C.Structure):
 ABI_VERSION = 2  # must equal skgs_abi_version() of the loaded library
 ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
+WARP_METHODS = {'LBS': 0, 'LBS_c': 1, 'largest': 2}
 
 # every symbol include/skgs_b200.h declares: (restype, argtypes)
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -93,6 +114,9 @@ _SIGNATURES = {
     'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 9),
     'skgs_fk_lbs_workspace_bytes': (C.c_size_t, [_i32]),
     'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),
+    'skgs_sp_lbs_workspace_bytes': (C.c_size_t, [_i32]),
+    'skgs_sp_lbs_forward': (C.c_int, [C.POINTER(Superpoints), _i32] + [_vp] * 9),
+    'skgs_sp_lbs_backward': (C.c_int, [C.POINTER(Superpoints), _i32] + [_vp] * 20),
     'skgs_assemble_forward': (C.c_int, [_i32] + [_vp] * 12),
     'skgs_assemble_backward': (C.c_int, [_i32] + [_vp] * 16),
     'skgs_image_loss_workspace_bytes': (C.c_size_t, [_i32, _i32]),
@@ -100,6 +124,11 @@ _SIGNATURES = {
                                   _vp]),
     'skgs_adam_step': (C.c_int, [C.POINTER(AdamTensor), _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_float,
                                  _vp, _vp, _vp]),
+    'skgs_densify_stats': (C.c_int, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'skgs_densify_workspace_bytes': (C.c_size_t, [_i32]),
+    'skgs_densify_plan': (C.c_int, [C.POINTER(DensifyConfig), _i32] + [_vp] * 11),
+    'skgs_densify_apply': (C.c_int, [C.POINTER(DensifyTensor), _i32, _i32] + [_vp] * 7),
+    'skgs_opacity_reset': (C.c_int, [_i32, _vp, _vp, _vp, C.c_float, _vp]),
     'skgs_joint_mlp_layout': (C.c_int, [C.POINTER(JointMlp), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     'skgs_joint_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(JointMlp)]),

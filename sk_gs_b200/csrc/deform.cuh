@@ -52,7 +52,9 @@ struct LbsOut {
 
 // K nearest joints of p (brute force over the shared-memory table, K-list by insertion in registers), the skinning
 // weights of the selected mode and the blend  d_xyz = sum_k w_k (R_k p + t_k) - p,  d_rot = sum w dq,  d_scale = sum w ds.
-template <int KT>
+// LARGEST (sp-stage warp method 'largest', networks/sk_gs.py:850-851,805-806,811-812): the mean follows the ONE
+// transform with the largest weight (first maximum, as torch.argmax), rotation / scale residuals stay blended.
+template <int KT, bool LARGEST = false>
 __device__ __forceinline__ void lbs_gaussian(const JointTable& jt, int M, int mode, float temperature,
                                              const float* __restrict__ sp_W_row, float px, float py, float pz,
                                              LbsOut<KT>& o) {
@@ -114,6 +116,16 @@ __device__ __forceinline__ void lbs_gaussian(const JointTable& jt, int M, int mo
   }
   const float winv = 1.0f / wsum;
   float ox = 0.f, oy = 0.f, oz = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  int kmax = 0;
+  if constexpr (LARGEST) {
+    float wmax = w[0] * winv;
+#pragma unroll
+    for (int k = 1; k < KT; k++)
+      if (w[k] * winv > wmax) {
+        wmax = w[k] * winv;
+        kmax = k;
+      }
+  }
 #pragma unroll
   for (int k = 0; k < KT; k++) {
     const float wk = w[k] * winv;
@@ -124,7 +136,11 @@ __device__ __forceinline__ void lbs_gaussian(const JointTable& jt, int M, int mo
     const float yx = R[0] * px + R[1] * py + R[2] * pz + jt.t[3 * a];
     const float yy = R[3] * px + R[4] * py + R[5] * pz + jt.t[3 * a + 1];
     const float yz = R[6] * px + R[7] * py + R[8] * pz + jt.t[3 * a + 2];
-    ox += wk * yx; oy += wk * yy; oz += wk * yz;
+    if constexpr (LARGEST) {
+      if (k == kmax) { ox = yx; oy = yy; oz = yz; }
+    } else {
+      ox += wk * yx; oy += wk * yy; oz += wk * yz;
+    }
     r0 += wk * jt.dq[4 * a]; r1 += wk * jt.dq[4 * a + 1]; r2 += wk * jt.dq[4 * a + 2]; r3 += wk * jt.dq[4 * a + 3];
     s0 += wk * jt.ds[3 * a]; s1 += wk * jt.ds[3 * a + 1]; s2 += wk * jt.ds[3 * a + 2];
   }

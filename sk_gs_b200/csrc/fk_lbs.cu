@@ -198,7 +198,7 @@ fk_table_kernel(skgs_skeleton sk, float* __restrict__ sk_T, float* __restrict__ 
   }
 }
 
-template <int KT>  // KT = K as a compile-time constant (1..8): the K-list lives in registers
+template <int KT, bool LARGEST = false>  // KT = K as a compile-time constant (1..8): the K-list lives in registers
 __global__ void __launch_bounds__(FK_THREADS)
 lbs_fwd_kernel(int M, int mode, float temperature, const float* __restrict__ table, const float* __restrict__ sp_W,
                int P, const float* __restrict__ xyz, float* __restrict__ d_xyz, float* __restrict__ d_rot,
@@ -212,7 +212,7 @@ lbs_fwd_kernel(int M, int mode, float temperature, const float* __restrict__ tab
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
     const float px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
     LbsOut<KT> o;
-    lbs_gaussian<KT>(jt, M, mode, temperature, sp_W ? sp_W + (size_t)i * M : nullptr, px, py, pz, o);
+    lbs_gaussian<KT, LARGEST>(jt, M, mode, temperature, sp_W ? sp_W + (size_t)i * M : nullptr, px, py, pz, o);
     d_xyz[3 * (size_t)i] = o.dx; d_xyz[3 * (size_t)i + 1] = o.dy; d_xyz[3 * (size_t)i + 2] = o.dz;
     *reinterpret_cast<float4*>(d_rot + 4 * (size_t)i) = make_float4(o.r0, o.r1, o.r2, o.r3);
     d_scale[3 * (size_t)i] = o.s0; d_scale[3 * (size_t)i + 1] = o.s1; d_scale[3 * (size_t)i + 2] = o.s2;
@@ -234,7 +234,7 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
                const float* __restrict__ weights, const int64_t* __restrict__ indices,
                const float* __restrict__ g_dxyz, const float* __restrict__ g_drot, const float* __restrict__ g_dscale,
                const float* __restrict__ g_w, float* __restrict__ dL_dsp_W, float* __restrict__ dL_dsp_W_knn,
-               float* __restrict__ jacc /*[M][NJ]*/) {
+               float* __restrict__ jacc /*[M][NJ]*/, int largest) {
   extern __shared__ float bsm[];
   const int M = sk.M, K = sk.K;
   float* s_pos = bsm;             // [M][3]
@@ -271,15 +271,21 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
     float w[MAXK], dw[MAXK];
     int idx[MAXK];
     float wdw = 0.f;
+    int kmax = 0;  // warp method 'largest': the mean follows the transform of the largest weight only
 #pragma unroll
     for (int k = 0; k < MAXK; k++)
       if (k < K) {
         w[k] = weights[(size_t)i * K + k];
+        if (w[k] > w[kmax]) kmax = k;
+      }
+#pragma unroll
+    for (int k = 0; k < MAXK; k++)
+      if (k < K) {
         const int a = idx[k] = (int)indices[(size_t)i * K + k];
         const float* Ta = s_T + 7 * a;
         const Quat q = {Ta[3], Ta[4], Ta[5], Ta[6]};
         const Vec3 y = q_rotate(q, p);
-        float d = G.x * (y.x + Ta[0]) + G.y * (y.y + Ta[1]) + G.z * (y.z + Ta[2]);
+        float d = largest ? 0.f : G.x * (y.x + Ta[0]) + G.y * (y.y + Ta[1]) + G.z * (y.z + Ta[2]);
         d += gr.x * s_dq[4 * a] + gr.y * s_dq[4 * a + 1] + gr.z * s_dq[4 * a + 2] + gr.w * s_dq[4 * a + 3];
         d += gs.x * s_ds[3 * a] + gs.y * s_ds[3 * a + 1] + gs.z * s_ds[3 * a + 2];
         if (g_w) d += g_w[(size_t)i * K + k];
@@ -287,7 +293,8 @@ lbs_bwd_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const flo
         wdw += w[k] * d;
         // per-joint sums: dt, dq (polynomial gradient, projected later in fk_bwd), d(sk_d_rot), d(sk_d_scale)
         float* acc = s_acc + NJ * a;
-        const Vec3 wG = {w[k] * G.x, w[k] * G.y, w[k] * G.z};
+        const float wa = largest ? (k == kmax ? 1.f : 0.f) : w[k];
+        const Vec3 wG = {wa * G.x, wa * G.y, wa * G.z};
         const Quat gq = q_rotate_grad_q(q, p, wG);
         atomicAdd(acc + 0, wG.x); atomicAdd(acc + 1, wG.y); atomicAdd(acc + 2, wG.z);
         atomicAdd(acc + 3, gq.x); atomicAdd(acc + 4, gq.y); atomicAdd(acc + 5, gq.z); atomicAdd(acc + 6, gq.w);
@@ -593,6 +600,7 @@ lbs_bwd_jm_kernel(skgs_skeleton sk, int P, const float* __restrict__ xyz, const 
   }
   // ---- FK backward as the tail of this kernel: the LAST CTA to get here sees every CTA's per-joint sums and runs the
   //      level-synchronous sweep through the kinematic chain itself (no second launch, no single-CTA kernel)
+  if (done == nullptr) return;  // sp-stage caller: its own per-superpoint tail kernel follows
   __shared__ uint32_t s_last;
   __threadfence();
   __syncthreads();
@@ -827,6 +835,99 @@ __global__ void assemble_bwd_kernel(int P, const float* __restrict__ scaling, co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// sp-stage: the same per-Gaussian kernels with the transform table coming from the per-superpoint SE3
+// the deformation network predicts instead of from forward kinematics.  Reference: `warp` networks/sk_gs.py:776-828,
+// `calc_LBS_weight` :751-774, called from `sp_stage` :830-856.  lietorch (un-vendored) supplies SE3.act = R(q) p + t
+// (my_ext/_C/include/lie.h:246) and, in backward, gradients w.r.t. the 7-vector projected onto the tangent space of
+// R^3 x S^3 at (t, q) - reproduced here by differentiating through q / |q|.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+sp_table_kernel(skgs_superpoints sp, float* __restrict__ spT, float* __restrict__ table) {
+  const int M = sp.M;
+  pdl_wait();
+  pdl_trigger();
+  float* pos = table;
+  float* tt = pos + 3 * M;
+  float* R = tt + 3 * M;
+  float* dq = R + 9 * M;
+  float* ds = dq + 4 * M;
+  float* aux = ds + 3 * M;
+  for (int a = threadIdx.x; a < M; a += blockDim.x) {
+    const Vec3 c = load_v(sp.sp_points + 3 * a);
+    const Quat raw = load_q(sp.sp_r + 4 * a);
+    const Quat q = q_normalize(raw);
+    Vec3 t = load_v(sp.sp_t + 3 * a);
+    if (sp.method == SKGS_WARP_LBS_C) {  // rotation about the superpoint: t + c + R(q)(-c)   (:797-798)
+      const Vec3 rc = q_rotate(q, {-c.x, -c.y, -c.z});
+      t = {t.x + c.x + rc.x, t.y + c.y + rc.y, t.z + c.z + rc.z};
+    }
+    if (spT != nullptr) {
+      spT[7 * a] = t.x; spT[7 * a + 1] = t.y; spT[7 * a + 2] = t.z;
+      spT[7 * a + 3] = raw.x; spT[7 * a + 4] = raw.y; spT[7 * a + 5] = raw.z; spT[7 * a + 6] = raw.w;
+    }
+    pos[3 * a] = c.x; pos[3 * a + 1] = c.y; pos[3 * a + 2] = c.z;
+    tt[3 * a] = t.x; tt[3 * a + 1] = t.y; tt[3 * a + 2] = t.z;
+    quat_to_rows(q, R + 9 * a);
+    const float* rot = sp.sp_rot ? sp.sp_rot : sp.sp_r;  // :818-821
+    for (int k = 0; k < 4; k++) dq[4 * a + k] = rot[4 * a + k];
+    for (int k = 0; k < 3; k++) ds[3 * a + k] = sp.sp_scale ? sp.sp_scale[3 * a + k] : 0.f;
+    float a0 = 0.f, a1 = 1.f;
+    if (sp.mode == SKGS_LBS_KERNEL || sp.mode == SKGS_LBS_WEIGHTED_KERNEL) {
+      const float r = expf(sp.sp_radius[a]);
+      a0 = 1.0f / (2.0f * r * r);
+      a1 = sp.mode == SKGS_LBS_WEIGHTED_KERNEL ? sigmoidf(sp.sp_weight[a]) : 1.0f;
+    }
+    aux[2 * a] = a0;
+    aux[2 * a + 1] = a1;
+  }
+}
+
+struct SpBwdOut {
+  const float* dL_dspT;  // direct gradient on the returned [M][7] or NULL
+  float *dL_dsp_points, *dL_dsp_t, *dL_dsp_r, *dL_dsp_rot, *dL_dsp_scale, *dL_dsp_radius, *dL_dsp_weight;
+};
+
+// per-superpoint tail of the backward: the per-joint sums of the LBS backward -> gradients of warp's inputs
+__global__ void __launch_bounds__(256)
+sp_bwd_kernel(skgs_superpoints sp, const float* __restrict__ jacc, SpBwdOut o) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= sp.M) return;
+  const float* acc = jacc + NJ * a;
+  Vec3 gt = {acc[0], acc[1], acc[2]};
+  Quat gq = {acc[3], acc[4], acc[5], acc[6]};
+  if (o.dL_dspT != nullptr) {
+    gt.x += o.dL_dspT[7 * a]; gt.y += o.dL_dspT[7 * a + 1]; gt.z += o.dL_dspT[7 * a + 2];
+    gq.x += o.dL_dspT[7 * a + 3]; gq.y += o.dL_dspT[7 * a + 4]; gq.z += o.dL_dspT[7 * a + 5];
+    gq.w += o.dL_dspT[7 * a + 6];
+  }
+  const Quat raw = load_q(sp.sp_r + 4 * a);
+  const float n = sqrtf(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z + raw.w * raw.w);
+  const Quat q = q_normalize(raw);
+  Vec3 gc = {acc[14], acc[15], acc[16]};  // through the squared distances of the weight function
+  if (sp.method == SKGS_WARP_LBS_C) {
+    const Vec3 c = load_v(sp.sp_points + 3 * a);
+    const Vec3 back = q_rotate_inv(q, gt);
+    gc.x += gt.x - back.x; gc.y += gt.y - back.y; gc.z += gt.z - back.z;
+    const Quat g1 = q_rotate_grad_q(q, {-c.x, -c.y, -c.z}, gt);
+    gq.x += g1.x; gq.y += g1.y; gq.z += g1.z; gq.w += g1.w;
+  }
+  Quat gr = q_normalize_bwd(q, n, gq);  // tangent-space projection (lietorch FromVec backward)
+  if (sp.sp_rot == nullptr) {            // d_rotation blends sp_r itself (:820-821): plain gradient
+    gr.x += acc[7]; gr.y += acc[8]; gr.z += acc[9]; gr.w += acc[10];
+  }
+  if (o.dL_dsp_points) { o.dL_dsp_points[3 * a] = gc.x; o.dL_dsp_points[3 * a + 1] = gc.y; o.dL_dsp_points[3 * a + 2] = gc.z; }
+  if (o.dL_dsp_t) { o.dL_dsp_t[3 * a] = gt.x; o.dL_dsp_t[3 * a + 1] = gt.y; o.dL_dsp_t[3 * a + 2] = gt.z; }
+  if (o.dL_dsp_r) { o.dL_dsp_r[4 * a] = gr.x; o.dL_dsp_r[4 * a + 1] = gr.y; o.dL_dsp_r[4 * a + 2] = gr.z; o.dL_dsp_r[4 * a + 3] = gr.w; }
+  if (o.dL_dsp_rot)
+    for (int k = 0; k < 4; k++) o.dL_dsp_rot[4 * a + k] = sp.sp_rot ? acc[7 + k] : 0.f;
+  if (o.dL_dsp_scale)
+    for (int k = 0; k < 3; k++) o.dL_dsp_scale[3 * a + k] = sp.sp_scale ? acc[11 + k] : 0.f;
+  if (o.dL_dsp_radius) o.dL_dsp_radius[a] = acc[17];
+  if (o.dL_dsp_weight) o.dL_dsp_weight[a] = acc[18];
+}
+
 static int fk_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -975,7 +1076,7 @@ int skgs_fk_lbs_backward(const skgs_skeleton* sk, int32_t P, const float* xyz, c
     {
       ProfScope prof_("lbs_bwd_kernel", st);
       lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(*sk, P, xyz, sk_T, weights, indices, dL_dd_xyz, dL_dd_rot,
-                                                   dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc);
+                                                   dL_dd_scale, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc, 0);
       SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
     }
   }
@@ -1036,6 +1137,143 @@ int skgs_assemble_backward(int32_t P, const float* scaling, const float* rotatio
   SKGS_CHECK_LAUNCH("assemble_bwd_kernel");
   }
   return SKGS_OK;
+}
+
+
+// ---- sp-stage LBS (f-4)
+static int check_superpoints(const skgs_superpoints* sp, int P) {
+  SKGS_CHECK_ARG(sp != nullptr, "superpoints are NULL");
+  SKGS_CHECK_ARG(sp->M >= 1 && sp->M <= 1024, "M=%d out of range [1,1024]", sp->M);
+  SKGS_CHECK_ARG(sp->K >= 1 && sp->K <= MAXK && sp->K <= sp->M, "K=%d must be in [1,%d] and <= M", sp->K, MAXK);
+  SKGS_CHECK_ARG(sp->mode >= 0 && sp->mode <= 3, "unknown LBS mode %d", sp->mode);
+  SKGS_CHECK_ARG(sp->method >= 0 && sp->method <= 2, "unknown warp method %d", sp->method);
+  SKGS_CHECK_ARG(sp->sp_points && sp->sp_t && sp->sp_r, "sp_points / sp_t / sp_r required");
+  SKGS_CHECK_ARG(sp->mode != SKGS_LBS_W || sp->sp_W || P == 0, "mode W needs sp_W");
+  SKGS_CHECK_ARG((sp->mode != SKGS_LBS_KERNEL && sp->mode != SKGS_LBS_WEIGHTED_KERNEL) || sp->sp_radius,
+                 "kernel modes need sp_radius");
+  SKGS_CHECK_ARG(sp->mode != SKGS_LBS_WEIGHTED_KERNEL || sp->sp_weight, "weighted_kernel needs sp_weight");
+  SKGS_CHECK_ARG(sp->mode != SKGS_LBS_DIST || sp->temperature > 0.f, "dist mode needs temperature > 0");
+  return SKGS_OK;
+}
+
+int skgs_sp_lbs_forward(const skgs_superpoints* sp, int32_t P, const float* points, float* d_points,
+                        float* d_rotation, float* d_scales, float* spT, float* weights, int64_t* indices,
+                        void* workspace, void* stream) {
+  int rc = check_superpoints(sp, P);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(P >= 0, "P < 0");
+  SKGS_CHECK_ARG(P == 0 || (points && d_points && d_rotation && d_scales && weights && indices),
+                 "NULL per-Gaussian buffer");
+  SKGS_CHECK_ARG(workspace != nullptr, "workspace (skgs_fk_lbs_workspace_bytes) is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* table = reinterpret_cast<float*>(workspace);
+  {
+    int threads = ((sp->M + 31) / 32) * 32;
+    threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+    ProfScope prof_("sp_table_kernel", st);
+    SKGS_CUDA(launch_pdl(sp_table_kernel, dim3(1), dim3(threads), 0, st, *sp, spT, table));
+    SKGS_CHECK_LAUNCH("sp_table_kernel");
+  }
+  if (P == 0) return SKGS_OK;
+  const size_t smem = (size_t)sp->M * JT_FLOATS * sizeof(float);
+  int grid = (P + FK_THREADS - 1) / FK_THREADS;
+  const int cap = fk_num_sms() * 8;
+  grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+  {
+    ProfScope prof_("lbs_fwd_kernel", st);
+#define SKGS_SP_LAUNCH(KK, LG)                                                                                         \
+  {                                                                                                                    \
+    static size_t smem_set = 0;                                                                                        \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                                         \
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_fwd_kernel<KK, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                 \
+    }                                                                                                                  \
+    SKGS_CUDA(launch_pdl(lbs_fwd_kernel<KK, LG>, dim3(grid), dim3(FK_THREADS), smem, st, sp->M, sp->mode,            \
+                         sp->temperature, (const float*)table, sp->sp_W, P, points, d_points, d_rotation, d_scales,   \
+                         weights, indices));                                                                           \
+  }
+#define SKGS_SP_CASE(KK)                                   \
+  case KK:                                                 \
+    if (sp->method == SKGS_WARP_LARGEST) SKGS_SP_LAUNCH(KK, true) else SKGS_SP_LAUNCH(KK, false) break;
+    switch (sp->K) {
+      SKGS_SP_CASE(1) SKGS_SP_CASE(2) SKGS_SP_CASE(3) SKGS_SP_CASE(4) SKGS_SP_CASE(5) SKGS_SP_CASE(6) SKGS_SP_CASE(7)
+      SKGS_SP_CASE(8)
+      default: break;
+    }
+#undef SKGS_SP_CASE
+#undef SKGS_SP_LAUNCH
+    SKGS_CHECK_LAUNCH("lbs_fwd_kernel");
+  }
+  return SKGS_OK;
+}
+
+int skgs_sp_lbs_backward(const skgs_superpoints* sp, int32_t P, const float* points, const float* spT,
+                         const float* weights, const int64_t* indices, const float* dL_dd_points,
+                         const float* dL_dd_rotation, const float* dL_dd_scales, const float* dL_dspT,
+                         const float* dL_dweights, float* dL_dsp_points, float* dL_dsp_t, float* dL_dsp_r,
+                         float* dL_dsp_rot, float* dL_dsp_scale, float* dL_dsp_W, float* dL_dsp_W_knn,
+                         float* dL_dsp_radius, float* dL_dsp_weight, void* workspace, void* stream) {
+  int rc = check_superpoints(sp, P);
+  if (rc) return rc;
+  SKGS_CHECK_ARG(workspace != nullptr && spT != nullptr, "workspace and spT are required");
+  SKGS_CHECK_ARG(P == 0 || (points && weights && indices), "NULL per-Gaussian buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* jacc = reinterpret_cast<float*>(workspace);
+  float* zeros = jacc + (size_t)sp->M * NJ + 16;  // 3 M zero floats standing in for an absent sp_scale
+  SKGS_CUDA(cudaMemsetAsync(jacc, 0, skgs_sp_lbs_workspace_bytes(sp->M), st));
+  // the per-Gaussian backward kernels see the superpoints as a skeleton without a kinematic chain
+  skgs_skeleton sk{};
+  sk.M = sp->M; sk.L = 0; sk.root = 0; sk.K = sp->K; sk.mode = sp->mode; sk.temperature = sp->temperature;
+  sk.joints = sp->sp_points; sk.sk_r = sp->sp_r; sk.sk_d_rot = sp->sp_rot ? sp->sp_rot : sp->sp_r;
+  sk.sk_d_scale = sp->sp_scale ? sp->sp_scale : zeros;
+  sk.sp_W = sp->sp_W; sk.sp_radius = sp->sp_radius; sk.sp_weight = sp->sp_weight;
+  if (P > 0 && sp->mode == SKGS_LBS_W && dL_dsp_W != nullptr)
+    SKGS_CUDA(cudaMemsetAsync(dL_dsp_W, 0, (size_t)P * sp->M * sizeof(float), st));
+  if (P > 0 && sp->M <= JM_MAX_M && sp->method != SKGS_WARP_LARGEST) {
+    const size_t smem = lbs_bwd_jm_smem_bytes(sp->M);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_bwd_jm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    int grid = (P + JM_CHUNK - 1) / JM_CHUNK;
+    const int cap = fk_num_sms() * 2;
+    grid = grid > cap ? cap : grid;
+    ProfScope prof_("lbs_bwd_kernel", st);
+    FkBwdOut none{};
+    SKGS_CUDA(launch_pdl(lbs_bwd_jm_kernel, dim3(grid), dim3(FK_THREADS), smem, st, sk, P, points, spT, weights,
+                         indices, dL_dd_points, dL_dd_rotation, dL_dd_scales, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc,
+                         (uint32_t*)nullptr, none));
+    SKGS_CHECK_LAUNCH("lbs_bwd_jm_kernel");
+  } else if (P > 0) {
+    const size_t smem = lbs_bwd_smem_bytes(sp->M);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      SKGS_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    int grid = (P + FK_THREADS - 1) / FK_THREADS;
+    const int cap = fk_num_sms() * 2;
+    grid = grid > cap ? cap : grid;
+    ProfScope prof_("lbs_bwd_kernel", st);
+    lbs_bwd_kernel<<<grid, FK_THREADS, smem, st>>>(sk, P, points, spT, weights, indices, dL_dd_points, dL_dd_rotation,
+                                                 dL_dd_scales, dL_dweights, dL_dsp_W, dL_dsp_W_knn, jacc,
+                                                 sp->method == SKGS_WARP_LARGEST ? 1 : 0);
+    SKGS_CHECK_LAUNCH("lbs_bwd_kernel");
+  }
+  {
+    ProfScope prof_("sp_bwd_kernel", st);
+    SpBwdOut o{dL_dspT, dL_dsp_points, dL_dsp_t, dL_dsp_r, dL_dsp_rot, dL_dsp_scale, dL_dsp_radius, dL_dsp_weight};
+    sp_bwd_kernel<<<(sp->M + 255) / 256, 256, 0, st>>>(*sp, jacc, o);
+    SKGS_CHECK_LAUNCH("sp_bwd_kernel");
+  }
+  return SKGS_OK;
+}
+
+size_t skgs_sp_lbs_workspace_bytes(int32_t M) {
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  const size_t fwd = m * JT_FLOATS * sizeof(float), bwd = (m * (NJ + 3) + 16) * sizeof(float);
+  return (fwd > bwd ? fwd : bwd) + 64;
 }
 
 }  // extern "C"

@@ -47,6 +47,8 @@ class TrainLoop:
         self.graph = None
         self._capture_args = None
         self.recaptures = 0
+        self.after_adam = None  # optional hook(out, grads) launched right after the Adam kernel (densify statistics)
+        self.extra_state = None  # optional callable -> tensors the hook mutates (restored after capture's warm-up)
 
     # ------------------------------------------------------------------------------------------------------ pieces
     def _adam(self, out, grads, grad_scale: float = 1.0, dynamic: bool = False):
@@ -61,6 +63,38 @@ class TrainLoop:
                       [self.lrs[n] for n in self.names], max(self.iteration, 1), self.betas[0], self.betas[1], self.eps,
                       grad_scale=grad_scale, knn_indices=knn, dynamic_hyper=self._hyper_dev if dynamic else None,
                       skip_flag_ptr=None if st is None else st.overflow_ptr)
+        if self.after_adam is not None:
+            self.after_adam(out, grads)
+
+    # ------------------------------------------------------------------------------------- densification (8 f-3)
+    def replace_gaussians(self, tensors):
+        """Install a new Gaussian set: `tensors` = {name: (param, exp_avg, exp_avg_sq)} for every per-Gaussian
+        parameter (what the reference's change_optimizer + setattr loop does, gaussian_splatting.py:515-563,571-572)."""
+        hp = self.hp
+        P_new = None
+        for n, (p, m, v) in tensors.items():
+            if n not in hp.params:
+                raise RuntimeError(f'replace_gaussians: unknown parameter {n!r}')
+            P_new = p.shape[0] if P_new is None else P_new
+            if p.shape[0] != P_new or p.shape[1:] != hp.params[n].shape[1:]:
+                raise RuntimeError(f'replace_gaussians: {n} has shape {tuple(p.shape)}')
+            hp.params[n] = p.requires_grad_(hp.params[n].requires_grad)
+            self.exp_avg[n], self.exp_avg_sq[n] = m, v
+        if 'shs' in tensors:
+            shs = hp.params['shs']
+            hp.params['f_dc'], hp.params['f_rest'] = shs.detach()[:, :1], shs.detach()[:, 1:]
+        missing = [n for n in ('xyz', 'shs', 'scaling', 'rotation', 'opacity', 'sp_W')
+                   if n in hp.params and hp.params[n].shape[0] != P_new]
+        if missing:
+            raise RuntimeError(f'replace_gaussians: {missing} still have the old number of Gaussians')
+
+    def recapture_after_resize(self):
+        """The number of Gaussians changed: every buffer of the captured graph has the wrong size - capture again."""
+        if self.graph is None or self._capture_args is None:
+            return
+        torch.cuda.synchronize(self.hp.device)
+        self.graph = None
+        self.capture(**self._capture_args)
 
     def _set_hyper(self):
         vals = adam_hyper([self.lrs[n] for n in self.names], self.iteration, *self.betas)
@@ -81,7 +115,7 @@ class TrainLoop:
         iterations capture needs are undone (parameters and moments restored), so `replay()` x n == `step()` x n."""
         self._capture_args = dict(view=view, target=target, target_host=target_host, uploads=uploads, headroom=headroom)
         state = [self.hp.params[n].data for n in self.names] + list(self.exp_avg.values()) + \
-            list(self.exp_avg_sq.values())
+            list(self.exp_avg_sq.values()) + (list(self.extra_state()) if self.extra_state is not None else [])
         saved = [t.clone() for t in state]
         it = self.iteration
         self.iteration = max(it, 1)

@@ -13,6 +13,10 @@ be imported UNMODIFIED from /root/reference.  Functions exercised (all torch, CP
   networks/losses/ssim.py, image_loss.py : SSIM_Loss, ImageLoss (+ autograd)    -> loss.npz
   torch.optim.Adam (the reference's optimizer, gaussian_splatting.py:445-453)   -> adam.npz
   networks/sk_gs.py                      : SimpleDeformationNetwork ('freq_torch' encoders, fp64) -> deform_net.npz
+  networks/sk_gs.py                      : calc_LBS_weight, warp (sp-stage; lietorch SE3/SO3 and pytorch3d knn_points
+                                           replaced by functional stand-ins written from lie.h:59-64,246) -> sp_stage.npz
+  networks/gaussian_splatting.py         : add_densification_stats, densify (clone + split), prune, reset_opacity with
+                                           change_optimizer on a real torch.optim.Adam                -> densify.npz
 """
 import importlib
 import importlib.abc
@@ -136,6 +140,8 @@ def main():
     make_loss()
     make_adam()
     make_deform_net()
+    make_sp_stage()
+    make_densify()
     print('golden vectors written to', OUT)
 
 
@@ -205,6 +211,200 @@ def make_deform_net():
             out[f'dw{ci}_{li}'] = grads[1 + 2 * li].numpy()
             out[f'db{ci}_{li}'] = grads[2 + 2 * li].numpy()
     np.savez_compressed(os.path.join(OUT, 'deform_net.npz'), n=np.int64(len(cases)), **out)
+
+
+# ---- functional stand-ins for the two un-vendored packages `warp` / `calc_LBS_weight` call into
+def _rot(q, p):
+    """my_ext/_C/include/lie.h:59-64 (the rotation lietorch's SO3 / SE3 act applies; q used as stored)."""
+    v, w = q[..., :3], q[..., 3:]
+    v, p = torch.broadcast_tensors(v, p)
+    uv = 2 * torch.linalg.cross(v, p)
+    return p + w * uv + torch.linalg.cross(v, uv)
+
+
+class _SO3Stub:
+    def __init__(self, data):
+        self.data = data
+
+    @classmethod
+    def InitFromVec(cls, v):
+        return cls(v)
+
+    def __getitem__(self, i):
+        return type(self)(self.data[i])
+
+    def act(self, p):
+        return _rot(self.data, p)
+
+    def vec(self):
+        return self.data
+
+
+class _SE3Stub(_SO3Stub):
+    def act(self, p):  # lie.h:246
+        return _rot(self.data[..., 3:], p) + self.data[..., :3]
+
+
+def _knn_points_stub(p1, p2, l1=None, l2=None, K=1):
+    """pytorch3d.ops.knn_points: K smallest squared distances, ascending (differentiable)."""
+    d2 = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+    idx = torch.argsort(d2, dim=-1, stable=True)[..., :K]
+    return torch.gather(d2, -1, idx), idx, None
+
+
+def make_sp_stage():
+    """`calc_LBS_weight` (networks/sk_gs.py:751-774) + `warp` (:776-828) of the reference class, called unbound on a
+    namespace that carries the attributes they read, the way `sp_stage` (:843-855) calls them; float64.  Gradients are
+    taken w.r.t. the PRE-normalisation rotation (sp_stage normalises at :847), where lietorch's tangent-projected
+    gradient and plain autograd agree."""
+    sk = importlib.import_module('networks.sk_gs')
+    sk.SE3, sk.SO3, sk.knn_points = _SE3Stub, _SO3Stub, _knn_points_stub
+    cls = sk.SkeletonGaussianSplatting
+    g = torch.Generator().manual_seed(20241017 + 400)
+    out, n = {}, 0
+    for mode in ('W', 'kernel', 'weighted_kernel', 'dist'):
+        for method in ('LBS', 'LBS_c', 'largest'):
+            for sep_rot in (True, False):
+                P, M, K = 61, 13, 4
+                dd = dict(dtype=torch.float64)
+                points = torch.randn(P, 3, generator=g, **dd) * 0.5
+                leaf = lambda *sh, scale=1.0: (torch.randn(*sh, generator=g, **dd) * scale).requires_grad_()  # noqa: E731
+                sp_points, sp_t, raw_r = leaf(M, 3, scale=0.5), leaf(M, 3, scale=0.1), leaf(M, 4, scale=0.3)
+                raw_g, sp_scale = leaf(M, 4, scale=0.3), leaf(M, 3, scale=0.05)
+                sp_W, sp_radius, sp_weight = leaf(P, M), leaf(M, scale=0.3), leaf(M)
+                bias = torch.tensor([0, 0, 0, 1.0], **dd)
+                sp_r = torch.nn.functional.normalize(raw_r + bias, dim=-1)
+                sp_rot = torch.nn.functional.normalize(raw_g + bias, dim=-1) if sep_rot else None
+                self = types.SimpleNamespace(
+                    num_knn=K, sk_is_init=True, training=True,
+                    _sp_radius=sp_radius if 'kernel' in mode else None,
+                    _sp_weight=sp_weight if mode == 'weighted_kernel' else None,
+                    kernel_radius=torch.exp(sp_radius), kernel_weight=torch.sigmoid(sp_weight),
+                    sp_W=sp_W if mode == 'W' else None)
+                w, idx = cls.calc_LBS_weight(self, points, sp_points, None, None, temperature=1.0)
+                if method == 'largest':  # :850-851
+                    self.p2sp = torch.gather(idx, -1, w.argmax(dim=-1, keepdim=True))[:, 0]
+                d_points, d_rotation, d_scales, spT = cls.warp(self, points, sp_points, sp_t, sp_r, sp_rot, sp_scale, w,
+                                                               idx, method)
+                cot = [torch.randn(t.shape, generator=g, **dd) for t in (d_points, d_rotation, d_scales, spT)]
+                loss = sum((t * c).sum() for t, c in zip((d_points, d_rotation, d_scales, spT), cot))
+                leaves = {'sp_points': sp_points, 'sp_t': sp_t, 'raw_r': raw_r, 'sp_scale': sp_scale}
+                if sep_rot:
+                    leaves['raw_g'] = raw_g
+                if mode == 'W':
+                    leaves['sp_W'] = sp_W
+                if 'kernel' in mode:
+                    leaves['sp_radius'] = sp_radius
+                if mode == 'weighted_kernel':
+                    leaves['sp_weight'] = sp_weight
+                grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+                grads = [torch.zeros_like(l_) if g_ is None else g_ for g_, l_ in zip(grads, leaves.values())]
+                pre = f'c{n}_'
+                out[pre + 'cfg'] = np.array([mode, method, str(int(sep_rot))])
+                for k_, v_ in dict(points=points, sp_points=sp_points, sp_t=sp_t, raw_r=raw_r, raw_g=raw_g,
+                                   sp_scale=sp_scale, sp_W=sp_W, sp_radius=sp_radius, sp_weight=sp_weight, w=w, idx=idx,
+                                   d_points=d_points, d_rotation=d_rotation, d_scales=d_scales, spT=spT,
+                                   cot0=cot[0], cot1=cot[1], cot2=cot[2], cot3=cot[3]).items():
+                    out[pre + k_] = v_.detach().numpy()
+                for k_, v_ in zip(leaves, grads):
+                    out[pre + 'grad_' + k_] = v_.numpy()
+                n += 1
+    np.savez_compressed(os.path.join(OUT, 'sp_stage.npz'), n=np.int64(n), K=np.int64(4), **out)
+
+
+def make_densify():
+    """The reference's densification bookkeeping (networks/gaussian_splatting.py:503-665) run UNMODIFIED on a small
+    Gaussian set with a real torch.optim.Adam holding non-trivial moments.  The methods are borrowed from the class and
+    bound to a light object that carries the attributes they touch (the full constructor needs the whole framework);
+    torch.normal is replaced by `noise * std` with a recorded standard-normal table so that the split samples can be
+    reproduced (:601-603)."""
+    gsm = importlib.import_module('networks.gaussian_splatting')
+    GS = gsm.GaussianSplatting
+
+    class Shim:
+        param_names_map = dict(GS.param_names_map)
+        use_so3 = False
+        scaling_activation_inverse = staticmethod(torch.log)
+        points = property(lambda self: self._xyz)
+        get_scaling = property(lambda self: torch.exp(self._scaling))
+        get_opacity = property(lambda self: torch.sigmoid(self._opacity))
+
+    for fn in ('add_densification_stats', 'prune_points', 'densification_postfix', 'densify_and_split',
+               'densify_and_clone', 'densify', 'prune', 'reset_opacity'):
+        setattr(Shim, fn, GS.__dict__[fn])
+    Shim.change_optimizer = staticmethod(GS.__dict__['change_optimizer'].__func__)
+
+    g = torch.Generator().manual_seed(20241017 + 500)
+    out, n = {}, 0
+    extent = 2.0
+    cases = [dict(densify=True, prune=False, screen=None), dict(densify=True, prune=True, screen=20.0),
+             dict(densify=False, prune=True, screen=20.0), dict(densify=True, prune=True, screen=None),
+             dict(densify=False, prune=True, screen=None)]
+    for case in cases:
+        P = 400
+        m = Shim()
+        m._xyz = torch.nn.Parameter(torch.randn(P, 3, generator=g) * 0.5)
+        m._features_dc = torch.nn.Parameter(torch.randn(P, 1, 3, generator=g))
+        m._features_rest = torch.nn.Parameter(torch.randn(P, 15, 3, generator=g) * 0.1)
+        m._scaling = torch.nn.Parameter(torch.randn(P, 3, generator=g) * 1.0 - 3.6)
+        m._rotation = torch.nn.Parameter(torch.randn(P, 4, generator=g))
+        m._opacity = torch.nn.Parameter(torch.randn(P, 1, generator=g) * 3.0 - 2.0)
+        names = Shim.param_names_map
+        opt = torch.optim.Adam([{'params': [getattr(m, k)], 'lr': 1e-3, 'name': v} for k, v in names.items()],
+                               eps=1e-15)
+        for k in names:  # one optimizer step so that the moments are not all zero
+            getattr(m, k).grad = torch.randn(getattr(m, k).shape, generator=g)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        m.xyz_gradient_accum, m.denom, m.max_radii2D = torch.zeros(P, 1), torch.zeros(P, 1), torch.zeros(P)
+        # three steps of statistics (:669-675)
+        stat_in = []
+        for _ in range(3):
+            radii = torch.randint(0, 40, (P,), generator=g, dtype=torch.int32) * (torch.rand(P, generator=g) > 0.3)
+            vs = torch.zeros(P, 3, requires_grad=True)
+            vs.grad = torch.randn(P, 3, generator=g) * 4e-4
+            mask = radii > 0
+            m.max_radii2D[mask] = torch.max(m.max_radii2D[mask], radii[mask].float())
+            m.add_densification_stats(vs, mask)
+            stat_in.append((radii.clone(), vs.grad.clone()))
+        pre = f'c{n}_'
+        before = {v: getattr(m, k).detach().clone() for k, v in names.items()}
+        state0 = {v: opt.state[getattr(m, k)] for k, v in names.items()}
+        for v_, t_ in before.items():
+            out[pre + 'in_' + v_] = t_.numpy()
+            out[pre + 'in_m_' + v_] = state0[v_]['exp_avg'].clone().numpy()
+            out[pre + 'in_v_' + v_] = state0[v_]['exp_avg_sq'].clone().numpy()
+        for j, (r_, g_) in enumerate(stat_in):
+            out[pre + f'radii{j}'], out[pre + f'vsgrad{j}'] = r_.numpy(), g_.numpy()
+        out[pre + 'stat_accum'], out[pre + 'stat_denom'] = m.xyz_gradient_accum.clone().numpy(), m.denom.clone().numpy()
+        out[pre + 'stat_radii'] = m.max_radii2D.clone().numpy()
+        noise = torch.randn(2 * P, 3, generator=g)
+        real_normal = torch.normal
+        torch.normal = lambda mean=None, std=None, **kw: noise[:std.shape[0]] * std
+        try:
+            with torch.no_grad():
+                if case['densify']:
+                    m.densify(opt, max_grad=0.0002, extent=extent, densify_percent_dense=0.01)
+                if case['prune']:
+                    m.prune(opt, min_opacity=0.005, extent=extent, max_screen_size=case['screen'],
+                            prune_percent_dense=0.1)
+        finally:
+            torch.normal = real_normal
+        out[pre + 'noise'] = noise.numpy()
+        out[pre + 'cfg'] = np.array([float(case['densify']), float(case['prune']), case['screen'] or 0.0, extent])
+        for k, v_ in names.items():
+            t_ = getattr(m, k)
+            out[pre + 'out_' + v_] = t_.detach().numpy()
+            out[pre + 'out_m_' + v_] = opt.state[t_]['exp_avg'].numpy()
+            out[pre + 'out_v_' + v_] = opt.state[t_]['exp_avg_sq'].numpy()
+        out[pre + 'out_accum'], out[pre + 'out_denom'] = m.xyz_gradient_accum.numpy(), m.denom.numpy()
+        out[pre + 'out_radii'] = m.max_radii2D.numpy()
+        with torch.no_grad():
+            m.reset_opacity(opt)
+        out[pre + 'reset_opacity'] = m._opacity.detach().numpy()
+        out[pre + 'reset_m'] = opt.state[m._opacity]['exp_avg'].numpy()
+        n += 1
+    np.savez_compressed(os.path.join(OUT, 'densify.npz'), n=np.int64(n), **out)
 
 
 def make_adam():

@@ -72,6 +72,84 @@ def test_fk_matches_reference_skeleton_warp_and_find_root():
             assert np.abs(M.numpy() - d[f'T_v0{i}']).max() <= 1e-12
 
 
+def _sp_case(d, i, dtype=torch.float64, device='cpu'):
+    """Inputs of case i of sp_stage.npz as leaves + the keyword arguments of oracle.fk_lbs.sp_stage / sp_lbs.sp_warp."""
+    mode, method, sep = (str(v) for v in d[f'c{i}_cfg'])
+    t = {k: torch.from_numpy(d[f'c{i}_{k}']).to(device=device, dtype=dtype) for k in
+         ('points', 'sp_points', 'sp_t', 'raw_r', 'raw_g', 'sp_scale', 'sp_W', 'sp_radius', 'sp_weight')}
+    leaves = {k: t[k].clone().requires_grad_() for k in t if k != 'points'}
+    bias = torch.tensor([0, 0, 0, 1.0], dtype=dtype, device=device)
+    sp_r = torch.nn.functional.normalize(leaves['raw_r'] + bias, dim=-1)          # networks/sk_gs.py:847
+    sp_rot = torch.nn.functional.normalize(leaves['raw_g'] + bias, dim=-1) if sep == '1' else None  # :848
+    kw = dict(K=int(d['K']), mode=mode, method=method, sp_W=leaves['sp_W'] if mode == 'W' else None,
+              sp_radius=leaves['sp_radius'] if 'kernel' in mode else None,
+              sp_weight=leaves['sp_weight'] if mode == 'weighted_kernel' else None, temperature=1.0)
+    return t['points'], leaves, sp_r, sp_rot, kw
+
+
+def test_sp_stage_matches_reference_warp_and_calc_lbs_weight():
+    """reference networks/sk_gs.py:751-774 (calc_LBS_weight) + :776-828 (warp), all 4 weight modes x 3 warp methods x
+    sep_rot on/off: outputs and the gradients of every input (rotation: w.r.t. the pre-normalisation vector)."""
+    d = np.load(os.path.join(G, 'sp_stage.npz'))
+    for i in range(int(d['n'])):
+        points, leaves, sp_r, sp_rot, kw = _sp_case(d, i)
+        outs = OF.sp_stage(points, leaves['sp_points'], leaves['sp_t'], sp_r, sp_rot, leaves['sp_scale'], **kw)
+        d_points, d_rotation, d_scales, spT, w, idx = outs
+        assert np.array_equal(idx.numpy(), d[f'c{i}_idx'])
+        for name, got in (('w', w), ('d_points', d_points), ('d_rotation', d_rotation), ('d_scales', d_scales),
+                          ('spT', spT)):
+            assert np.abs(got.detach().numpy() - d[f'c{i}_{name}']).max() <= 1e-12, (i, name)
+        loss = sum((o * torch.from_numpy(d[f'c{i}_cot{j}'])).sum() for j, o in
+                   enumerate((d_points, d_rotation, d_scales, spT)))
+        names = [k[len(f'c{i}_grad_'):] for k in d.files if k.startswith(f'c{i}_grad_')]
+        grads = torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True)
+        for n, g in zip(names, grads):
+            ref = d[f'c{i}_grad_{n}']
+            got = np.zeros_like(ref) if g is None else g.numpy()
+            assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (i, n)
+
+
+DENSIFY_NAMES = ('xyz', 'f_dc', 'f_rest', 'scaling', 'rotation', 'opacity')
+
+
+def _densify_case(d, i):
+    """Inputs of case i of densify.npz: ({name: (param, exp_avg, exp_avg_sq)}, stats, config keywords, noise)."""
+    pre = f'c{i}_'
+    t = {n: tuple(torch.from_numpy(d[pre + k + n]) for k in ('in_', 'in_m_', 'in_v_')) for n in DENSIFY_NAMES}
+    dens, prune, screen, extent = (float(v) for v in d[pre + 'cfg'])
+    kw = dict(do_densify=bool(dens), do_prune=bool(prune), grad_threshold=0.0002, densify_extent=0.01 * extent,
+              min_opacity=0.005, max_screen_size=screen, prune_extent=0.1 * extent)
+    return t, kw, torch.from_numpy(d[pre + 'noise'])
+
+
+def test_densify_matches_reference_adaptive_control():
+    """reference networks/gaussian_splatting.py:503-513 (statistics), :640-645 densify = clone :624-638 + split :589-622,
+    :653-660 prune, :662-665 reset_opacity, with change_optimizer (:515-563) acting on a real torch.optim.Adam."""
+    from oracle import densify as OD
+    d = np.load(os.path.join(G, 'densify.npz'))
+    for i in range(int(d['n'])):
+        pre = f'c{i}_'
+        t, kw, noise = _densify_case(d, i)
+        P = t['xyz'][0].shape[0]
+        accum, denom, radii = torch.zeros(P), torch.zeros(P), torch.zeros(P)
+        for j in range(3):
+            OD.add_densification_stats(accum, denom, radii, torch.from_numpy(d[pre + f'radii{j}']),
+                                       torch.from_numpy(d[pre + f'vsgrad{j}']))
+        assert np.array_equal(accum.numpy(), d[pre + 'stat_accum'][:, 0])
+        assert np.array_equal(denom.numpy(), d[pre + 'stat_denom'][:, 0])
+        assert np.array_equal(radii.numpy(), d[pre + 'stat_radii'])
+        out, accum, denom, radii = OD.densify_and_prune(t, accum, denom, radii, noise=noise, **kw)
+        for n in DENSIFY_NAMES:
+            for k, j in (('out_', 0), ('out_m_', 1), ('out_v_', 2)):
+                ref = d[pre + k + n]
+                assert out[n][j].shape == ref.shape, (i, n, k)
+                assert np.abs(out[n][j].numpy() - ref).max() <= 1e-6, (i, n, k)
+        assert np.array_equal(accum.numpy(), d[pre + 'out_accum'].reshape(-1))
+        assert np.array_equal(radii.numpy(), d[pre + 'out_radii'])
+        assert np.abs(OD.reset_opacity(out['opacity'][0]).numpy() - d[pre + 'reset_opacity']).max() <= 1e-6
+        assert np.abs(d[pre + 'reset_m']).max() == 0
+
+
 def test_camera_matches_reference_perspective():
     """reference my_ext/ops_3d/coord_trans_opencv.py:203-239."""
     d = np.load(os.path.join(G, 'cam.npz'))
