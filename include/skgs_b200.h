@@ -108,12 +108,14 @@ typedef struct skgs_raster_layout {
   size_t vals_b;         /* uint32 [R_cap] */
   size_t sort_hist;      /* uint32 [8][256] digit histograms */
   size_t sort_status;    /* uint32 [tiles_of_keys][256] look-back words (tagged by pass) */
+  size_t tile_counts;    /* int32 [gy+1][gx+1] difference grid of the tile rectangles; its 2-D prefix sum = keys per tile */
+  size_t tile_cursors;   /* uint32 [tiles]  fill level of every tile segment during the scatter pass */
   /* img */
   size_t ranges;         /* uint2  [tiles]  [start, end) of every screen tile in the sorted list, (0, 0) if empty */
   size_t n_contrib;      /* uint32 [H*W] */
   size_t final_T;        /* float  [H*W] */
   size_t tile_order;     /* uint4  [tiles]  (tile, start, end, -) by decreasing list length: work order of compositing */
-  size_t work_counters;  /* uint32 [2]      work tickets of the forward / backward compositing kernels */
+  size_t work_counters;  /* uint32 [8]      work tickets: [0] forward / [1] backward compositing, [2..4] per-tile sort */
 } skgs_raster_layout;
 
 /* Lives at geom + layout.header; written on the device, never read by the library on the host.

@@ -66,7 +66,7 @@ def densify_and_prune(tensors: Dict[str, Triple], grad_accum: Tensor, denom: Ten
         t = _cat(t, {n: p[sel] for n, (p, _, _) in t.items()})
         # split (:589-622)
         P1 = t['xyz'][0].shape[0]
-        padded = torch.zeros(P1)
+        padded = torch.zeros(P1, device=grads.device)
         padded[:grads.shape[0]] = grads
         scale = torch.exp(t['scaling'][0])
         sel = (padded >= grad_threshold) & (scale.amax(dim=1) > densify_extent)
@@ -80,7 +80,7 @@ def densify_and_prune(tensors: Dict[str, Triple], grad_accum: Tensor, denom: Ten
         t = _cat(t, new)
         t = _keep(t, ~torch.cat([sel, sel.new_zeros(2 * ns)]))
         P2 = t['xyz'][0].shape[0]
-        grad_accum, denom, max_radii2D = torch.zeros(P2), torch.zeros(P2), torch.zeros(P2)  # :583-586
+        grad_accum, denom, max_radii2D = (torch.zeros(P2, device=grads.device) for _ in range(3))  # :583-586
     if do_prune:  # :653-660
         mask = torch.sigmoid(t['opacity'][0]).reshape(-1) < min_opacity
         if max_screen_size and max_screen_size > 0:

@@ -25,7 +25,8 @@ class RasterSettings(C.Structure):
 
 _LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
                   'rgbd', 'cull', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads',
-                  'keys_a', 'vals_a', 'keys_b', 'vals_b', 'sort_hist', 'sort_status', 'ranges', 'n_contrib',
+                  'keys_a', 'vals_a', 'keys_b', 'vals_b', 'sort_hist', 'sort_status', 'tile_counts', 'tile_cursors',
+                  'ranges', 'n_contrib',
                   'final_T', 'tile_order', 'work_counters']
 
 
@@ -84,7 +85,7 @@ class JointMlp(C.Structure):
     ]
 
 
-ABI_VERSION = 2  # must equal skgs_abi_version() of the loaded library
+ABI_VERSION = 3  # must equal skgs_abi_version() of the loaded library
 ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
 WARP_METHODS = {'LBS': 0, 'LBS_c': 1, 'largest': 2}

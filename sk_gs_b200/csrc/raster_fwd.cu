@@ -75,12 +75,15 @@ struct Emit {
 struct BinningOut {            // where the emitting kernel writes; all NULL in the geometry-only variant
   uint64_t* keys;              // buffer a
   uint32_t* vals;
-  uint32_t* hist;              // [passes][256]
+  uint32_t* hist;              // [passes][256] (radix binning)
+  uint32_t* tile_counts;       // [(gy+1)][(gx+1)] 2-D difference grid of the tile rectangles (tile-segmented binning:
+                               // its prefix sum is the number of keys per tile); NULL selects the radix bookkeeping
   uint2* ranges;               // [tiles] reset to (RANGE_UNSET, 0)
   uint32_t* counters;          // [2] compositing work tickets, reset to 0
   uint32_t R_cap;
   int passes;
   int tiles;
+  int cell_stride;             // ints between two cells of the difference grid
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -274,7 +277,18 @@ __device__ __forceinline__ void emit_warp(int lane, const Emit& e, uint32_t id, 
   if ((uint64_t)wbase + wtotal > (uint64_t)b.R_cap) {  // arena too small: flag, keep what fits out of bounds-safe
     if (lane == 0) hdr->overflow = 1;
   }
-  if (e.cnt > 0) {  // depth digits: the same for all of this Gaussian's keys
+  const bool by_tile = b.tile_counts != nullptr;
+  if (by_tile && e.cnt > 0) {
+    // +1 on the rectangle [x0, x0+w) x [y0, y0+h) as four corner updates: 4 atomics per Gaussian instead of one per
+    // key, and a tile that thousands of Gaussians cover is not one hot address (their corners are spread out)
+    int* dg = reinterpret_cast<int*>(b.tile_counts);
+    const int gs = gx + 1, h = (int)e.cnt / e.w, cs = b.cell_stride;
+    atomicAdd(&dg[(e.y0 * gs + e.x0) * cs], 1);
+    atomicAdd(&dg[(e.y0 * gs + e.x0 + e.w) * cs], -1);
+    atomicAdd(&dg[((e.y0 + h) * gs + e.x0) * cs], -1);
+    atomicAdd(&dg[((e.y0 + h) * gs + e.x0 + e.w) * cs], 1);
+  }
+  if (!by_tile && e.cnt > 0) {  // depth digits: the same for all of this Gaussian's keys
 #pragma unroll
     for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((e.dbits >> (8 * p)) & 255u)], e.cnt);
   }
@@ -302,6 +316,7 @@ __device__ __forceinline__ void emit_warp(int lane, const Emit& e, uint32_t id, 
         b.vals[slot] = g_id;
       }
     }
+    if (by_tile) continue;
     // tile digits: neighbouring slots mostly share the high digit -> aggregate equal digits before the atomic
     const uint32_t act = __ballot_sync(FULL, valid);
     for (int p = 4; p < b.passes; p++) {
@@ -317,6 +332,7 @@ __device__ __forceinline__ void emit_warp(int lane, const Emit& e, uint32_t id, 
 // ranges), the others ping-pong a -> b -> a ...; final_buf = where the sorted lists end up.
 __device__ __forceinline__ void finish_emission(int tid, int nthreads, uint32_t* s_hist, const BinningOut& b,
                                                 skgs_raster_header* hdr, uint32_t num_ctas, uint32_t* s_flag) {
+  if (b.tile_counts != nullptr) return;  // tile-segmented binning: the per-tile counts are all the next stage needs
   __syncthreads();
   for (int k = tid; k < b.passes * 256; k += nthreads) {
     const uint32_t c = s_hist[k];
@@ -914,6 +930,8 @@ static int binning_out(const RasterParams& rp, char* binning, char* img, const s
   b.keys = reinterpret_cast<uint64_t*>(binning + lay.keys_a);
   b.vals = reinterpret_cast<uint32_t*>(binning + lay.vals_a);
   b.hist = reinterpret_cast<uint32_t*>(binning + lay.sort_hist);
+  b.tile_counts = tile_sort_enabled() ? reinterpret_cast<uint32_t*>(binning + lay.tile_counts) : nullptr;
+  b.cell_stride = tile_cell_stride();
   b.ranges = reinterpret_cast<uint2*>(img + lay.ranges);
   b.counters = reinterpret_cast<uint32_t*>(img + lay.work_counters);
   b.R_cap = (uint32_t)R_cap;
@@ -1040,6 +1058,7 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (bo.tile_counts != nullptr) return launch_tile_binning(rp, geom, binning, img, lay, R_cap, R_hint, st);
   static bool attr_set = false;
   if (!attr_set) {
     SKGS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -107,9 +107,7 @@ def test_binning_bit_exact(name, P, seed, path):
     keys, plist = _sorted(st)
     h = st.header()
     assert int(h.num_rendered) == R and int(h.overflow) == 0
-    # the depth's sign / exponent byte is the same for every key of these scenes: that pass must have been skipped
-    # (depths lie in [2, 8): top byte 0x40); the pass over the top tile bits is never skipped: it writes the ranges
-    assert int(h.sort_plan[3]) & 1 == 1 and int(h.sort_plan[4]) & 1 == 0
+    assert int(h.final_buf) == 0  # tile-segmented binning leaves the sorted lists in keys_a / vals_a
     tiles = b.ranges.shape[0]
     ranges = arena_view(st.img, lay.ranges, torch.int32, 2 * tiles).view(tiles, 2).cpu().numpy().view(np.uint32)
     assert np.array_equal(keys, b.keys)
@@ -120,20 +118,22 @@ def test_binning_bit_exact(name, P, seed, path):
     assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
 
 
-def test_sort_long_tiles_and_depth_ties():
-    """Very long tile lists (> 8192 entries) and duplicated Gaussians: exactly equal depths must come out in ascending
-    Gaussian id (= emission order of the stable reference sort)."""
-    sc = S.make_scene('c1', P=12000, seed=17)
+@pytest.mark.parametrize('P,longest', [(12000, 8192), (60000, 3 * 16384)])
+def test_sort_long_tiles_and_depth_ties(P, longest):
+    """Very long tile lists and duplicated Gaussians: exactly equal depths must come out in ascending Gaussian id
+    (= emission order of the stable reference sort).  > 8192 entries: the 16384-entry shared-memory configuration of the
+    per-tile sort; > 3 x 16384: sorted chunks + merge passes."""
+    sc = S.make_scene('c1', P=P, seed=17)
     cam = sc.cameras[0]
     cam.W, cam.H = 48, 40
     cam.tanfovy = cam.tanfovx * cam.H / cam.W
     sc.scaling = sc.scaling + 2.0
-    sc.xyz[6000:] = sc.xyz[:6000]  # exact duplicates (same skinning weights too) -> exact depth ties
-    sc.sp_W[6000:] = sc.sp_W[:6000]
+    sc.xyz[P // 2:] = sc.xyz[:P // 2]  # exact duplicates (same skinning weights too) -> exact depth ties
+    sc.sp_W[P // 2:] = sc.sp_W[:P // 2]
     net, _, _ = oracle_deform(sc)
     net = {k: v.detach() for k, v in net.items()}
     _, img, g, b = _oracle_forward(sc, net)
-    assert (b.ranges[:, 1] - b.ranges[:, 0]).max() > 8192
+    assert (b.ranges[:, 1] - b.ranges[:, 0]).max() > longest
     d = g.depths[b.point_list]
     assert (np.diff(d) == 0).sum() > 1000
     for _ in range(2):  # first call of the shape: split path; second: keys emitted by the preprocess kernel
