@@ -186,9 +186,8 @@ class Runner:
         if world > 1:
             self.arena = (GradArena if args.allreduce == 'nccl' else SymmGradArena)(shapes, dev, order=list(shapes))
             if getattr(self.arena, 'multimem', False):
-                self.exchange_kind = 'NVLS multimem all-reduce kernel over symmetric memory' + \
-                    (', both cross-GPU barriers inside the launch' if getattr(self.arena, 'synced', False)
-                     and args.exchange == 'synced' else ' between two signal-pad barrier kernels')
+                self.exchange_kind = 'NVLS multimem all-reduce kernel over symmetric memory between two signal-pad ' \
+                                     'barrier kernels' 
             else:
                 self.exchange_kind = 'NCCL all-reduce'
         elif multi_view:
@@ -209,15 +208,9 @@ class Runner:
             return
         a = self.arena
         if self.split_exchange:  # the rasterizer-side blocks were reduced under the LBS / FK backward (mid_backward)
-            if self.args.exchange == 'synced':   # one launch: barrier + reduce + barrier (covers the first range too)
-                a.allreduce_range_synced(a.block_start('sp_W'), a.flat_padded.numel(), slot=1, exit_barrier=True)
-            else:
-                a.allreduce_range(a.block_start('sp_W'), a.flat_padded.numel(), channel=1)
+            a.allreduce_range(a.block_start('sp_W'), a.flat_padded.numel(), channel=1)
         else:
-            if getattr(a, 'synced', False) and self.args.exchange == 'synced':
-                a.allreduce_range_synced(0, a.flat_padded.numel(), slot=0)
-            else:
-                a.allreduce(chunks=1)
+            a.allreduce(chunks=1)
             self._allreduce_max(out['radii'])
 
     def after_forward(self, radii):
@@ -234,12 +227,7 @@ class Runner:
         main = torch.cuda.current_stream(self.dev)
         self.side2.wait_stream(main)
         with torch.cuda.stream(self.side2):
-            if self.args.exchange == 'synced':
-                # no exit barrier: every rank's second range (exchange(), after the join below) starts behind it
-                self.arena.allreduce_range_synced(0, self.arena.block_start('sp_W'), slot=0, exit_barrier=False,
-                                                  max_blocks=self.args.mm_blocks)
-            else:
-                self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0)
+            self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0)
         return lambda: main.wait_stream(self.side2)
 
     def capture(self, e2e: bool):
@@ -1022,10 +1010,6 @@ def main():
     ap.add_argument('--no-iteration', action='store_true', help='skip the MLP+loss+Adam full-iteration section')
     ap.add_argument('--no-workloads', action='store_true', help='skip the ns / c3 / c4 / c5 section')
     ap.add_argument('--headline-only', action='store_true', help='only value / e2e / kernels (quick runs)')
-    ap.add_argument('--exchange', default='synced', choices=['synced', 'barriers'],
-                    help='multimem exchange: one launch with both cross-GPU barriers inside (synced), or the bare '
-                         'kernel between two symmetric-memory barrier kernels')
-    ap.add_argument('--mm-blocks', type=int, default=0, help='grid cap of the overlapped all-reduce (0: default)')
     ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
                     help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
     args = ap.parse_args()

@@ -101,14 +101,14 @@ typedef struct skgs_raster_layout {
   size_t scan_state;     /* uint64 [ceil(P/256)+1] look-back words of the fused scan */
   size_t geom_grads;     /* float  [P][12] packed backward accumulators: mean2D.xy conic.abc opacity depth - rgb -
                                          (zero outside the composite-bwd -> preprocess-bwd window) */
-  /* binning (capacity R_cap entries): two physical key/value buffers the radix passes ping-pong between */
-  size_t keys_a;         /* uint64 [R_cap]  (tile << 32) | depth bits, emission order */
-  size_t vals_a;         /* uint32 [R_cap]  Gaussian ids, emission order */
-  size_t keys_b;         /* uint64 [R_cap] */
-  size_t vals_b;         /* uint32 [R_cap] */
-  size_t sort_hist;      /* uint32 [8][256] digit histograms */
-  size_t sort_status;    /* uint32 [tiles_of_keys][256] look-back words (tagged by pass) */
-  size_t tile_counts;    /* int32 [gy+1][gx+1] difference grid of the tile rectangles; its 2-D prefix sum = keys per tile */
+  /* binning (capacity R_cap entries) */
+  size_t keys;           /* uint64 [R_cap]  (tile << 32) | depth bits: emission order, after the forward SORTED by
+                                            (tile, depth), stable - the list cub::DeviceRadixSort::SortPairs produces in
+                                            the reference (gaussian_rasterizer_forward.cu:224-229) */
+  size_t vals;           /* uint32 [R_cap]  Gaussian ids, same order: after the forward the reference's point_list */
+  size_t tile_pairs;     /* uint64 [R_cap]  scratch: the per-tile segments (depth bits << 32 | Gaussian id) */
+  size_t tile_grid;      /* int32 [gy+1][gx+1] x 32: 2-D difference grid of the tile rectangles (one 128-byte line per
+                                            cell); its prefix sum is the number of keys per tile */
   size_t tile_cursors;   /* uint32 [tiles]  fill level of every tile segment during the scatter pass */
   /* img */
   size_t ranges;         /* uint2  [tiles]  [start, end) of every screen tile in the sorted list, (0, 0) if empty */
@@ -119,26 +119,19 @@ typedef struct skgs_raster_layout {
 } skgs_raster_layout;
 
 /* Lives at geom + layout.header; written on the device, never read by the library on the host.
- * After the forward the lists sorted by (tile, depth) - stable, identical to cub::DeviceRadixSort::SortPairs on the
- * low 32 + getHigherMsb(tiles) key bits (reference gaussian_rasterizer_forward.cu:224-229) - are keys_a / vals_a if
- * final_buf == 0, keys_b / vals_b if final_buf == 1: a radix pass whose digit is the same for every key (typically the
- * sign / exponent byte of the depth) is skipped on the device, so the parity of executed passes is data dependent. */
+ * After the forward the sorted lists are layout.keys / layout.vals. */
 typedef struct skgs_raster_header {
   uint32_t num_rendered;  /* R = sum tiles_touched (may exceed R_cap) */
   uint32_t num_visible;   /* Gaussians with radius > 0 */
   uint32_t scan_ticket;   /* internal */
   uint32_t overflow;      /* 1 if R > R_cap: the image of this call is INVALID, re-run with a larger binning arena */
-  uint32_t sort_ticket[8]; /* internal */
-  uint32_t sort_plan[8];  /* per radix pass: bit 0 = skipped, bit 1 = source buffer (0: a, 1: b) */
-  uint32_t final_buf;     /* buffer that holds the sorted lists: 0 = keys_a / vals_a, 1 = keys_b / vals_b */
-  uint32_t emit_done;     /* internal */
-  uint32_t reserved[10];
+  uint32_t reserved[28];
 } skgs_raster_header;
 
 SKGS_API int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skgs_raster_layout* out);
 
-/* Forward: preprocess (+ fused prefix sum + key emission with all digit histograms, ONE kernel) -> onesweep radix sort
- * (constant digits skipped on the device, the last pass writes the tile ranges) -> tile order -> per-tile compositing.
+/* Forward: preprocess (+ fused prefix sum + key emission + tile-rectangle counting, ONE kernel) -> tile plan (ranges,
+ * work order) -> scatter into per-tile segments -> per-tile sort in shared memory -> per-tile compositing.
  * Exactly one of shs / colors_precomp and one of (scales, rotations) / cov3D_precomp must be non-NULL (same rule as
  * networks/renderer/gaussian_render.py:250-255).
  *   means3D [P][3], shs [P][M][3], colors_precomp [P][3], opacities [P], scales [P][3], rotations [P][4], cov3D_precomp [P][6]
@@ -494,18 +487,6 @@ SKGS_API int skgs_joint_mlp_backward(const skgs_joint_mlp* net, const float* dL_
  * same stream.  The reference has no counterpart (its DDP wiring is unused, my_ext/framework.py:339-357). */
 SKGS_API int skgs_multimem_allreduce(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world, void* stream);
 
-/* The same all-reduce with BOTH cross-GPU barriers inside the one launch (fused compute + synchronisation over NVLink
- * peer memory): block 0 exchanges an epoch flag with every peer through the symmetric-memory signal pads
- * (`signal_pads_dev`: device array of `world` pointers, one pad per rank, e.g. handle.signal_pad_ptrs_dev; the kernel
- * uses the 2 * world uint32 words [channel * world, (channel + 2) * world) of every pad) before any block reduces, and
- * the last block to finish does the same after its stores are fenced - unless `exit_barrier` == 0, for a range whose
- * completion is covered by a later synced call on the same stream of every rank.
- * `ctrl`: 16 bytes of zero-initialised device memory private to this (arena, channel) pair; it carries the epoch, so a
- * captured CUDA graph can be replayed.  ctrl[3] != 0 afterwards means a peer never arrived (result invalid, no hang).
- * `max_blocks` (> 0) caps the grid, e.g. for a call that overlaps other kernels. */
-SKGS_API int skgs_multimem_allreduce_synced(void* multicast_ptr, int64_t numel, int32_t rank, int32_t world,
-                                            void* const* signal_pads_dev, int32_t channel, void* ctrl,
-                                            int32_t exit_barrier, int32_t max_blocks, void* stream);
 
 /* Multi-view steps: the reference loops over the views of a step and autograd SUMS their gradients
  * (networks/sk_gs.py:1220); the MAX of the screen radii over the views feeds max-radius tracking

@@ -25,8 +25,7 @@ class RasterSettings(C.Structure):
 
 _LAYOUT_FIELDS = ['geom_bytes', 'binning_bytes', 'img_bytes', 'header', 'means2D', 'depths', 'cov3D', 'conic_opacity',
                   'rgbd', 'cull', 'clamped', 'tiles_touched', 'point_offsets', 'scan_state', 'geom_grads',
-                  'keys_a', 'vals_a', 'keys_b', 'vals_b', 'sort_hist', 'sort_status', 'tile_counts', 'tile_cursors',
-                  'ranges', 'n_contrib',
+                  'keys', 'vals', 'tile_pairs', 'tile_grid', 'tile_cursors', 'ranges', 'n_contrib',
                   'final_T', 'tile_order', 'work_counters']
 
 
@@ -37,8 +36,7 @@ class RasterLayout(C.Structure):
 class RasterHeader(C.Structure):
     """struct skgs_raster_header (lives at geom + layout.header)."""
     _fields_ = [('num_rendered', C.c_uint32), ('num_visible', C.c_uint32), ('scan_ticket', C.c_uint32),
-                ('overflow', C.c_uint32), ('sort_ticket', C.c_uint32 * 8), ('sort_plan', C.c_uint32 * 8),
-                ('final_buf', C.c_uint32), ('emit_done', C.c_uint32), ('reserved', C.c_uint32 * 10)]
+                ('overflow', C.c_uint32), ('reserved', C.c_uint32 * 28)]
 
 
 class Skeleton(C.Structure):
@@ -85,7 +83,7 @@ class JointMlp(C.Structure):
     ]
 
 
-ABI_VERSION = 3  # must equal skgs_abi_version() of the loaded library
+ABI_VERSION = 4  # must equal skgs_abi_version() of the loaded library
 ADAM_MAX_TENSORS = 16
 LBS_MODES = {'W': 0, 'kernel': 1, 'weighted_kernel': 2, 'dist': 3}
 WARP_METHODS = {'LBS': 0, 'LBS_c': 1, 'largest': 2}
@@ -136,7 +134,6 @@ _SIGNATURES = {
     'skgs_joint_mlp_forward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_joint_mlp_backward': (C.c_int, [C.POINTER(JointMlp)] + [_vp] * 7),
     'skgs_multimem_allreduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
-    'skgs_multimem_allreduce_synced': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
     'skgs_accumulate_f32': (C.c_int, [_vp, _vp, _i64, _vp]),
     'skgs_max_i32': (C.c_int, [_vp, _vp, _i64, _vp]),
 }

@@ -34,15 +34,6 @@ bool pdl_enabled() {
   return on == 1;
 }
 
-bool tile_sort_enabled() {  // SKGS_SORT=radix selects the device-wide radix sort (A/B and fallback), default: tile
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("SKGS_SORT");
-    on = (e != nullptr && e[0] == 'r') ? 0 : 1;
-  }
-  return on == 1;
-}
-
 int tile_cell_stride() {  // ints between two cells of the tile difference grid (SKGS_CELL_STRIDE; tuning)
   static int v = 0;
   if (v == 0) {
@@ -77,7 +68,6 @@ void prof_end(cudaStream_t st) {
 
 int sort_passes(int gx, int gy);
 
-constexpr int OS_TILE_KEYS = 2048;  // lower bound of OS_TILE in raster_fwd.cu (sizes the look-back words)
 constexpr size_t ARENA_ALIGN = 256;
 
 static int fill_params(const skgs_raster_settings* s, int P, int M, RasterParams& rp) {
@@ -134,7 +124,7 @@ using namespace skgs;
 extern "C" {
 
 const char* skgs_last_error(void) { return g_err; }
-int skgs_abi_version(void) { return 3; }
+int skgs_abi_version(void) { return 4; }
 int skgs_built_for_sm(void) { return 100; }
 uint64_t skgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -183,7 +173,7 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   SKGS_CHECK_ARG(out != nullptr, "layout is NULL");
   SKGS_CHECK_ARG(P >= 0 && W > 0 && H > 0 && R_cap >= 0, "bad sizes P=%d W=%d H=%d R_cap=%lld", P, W, H,
                  (long long)R_cap);
-  SKGS_CHECK_ARG(R_cap < (1ll << 27), "R_cap=%lld exceeds the 2^27 entries of the sort's look-back word",
+  SKGS_CHECK_ARG(R_cap < (1ll << 31), "R_cap=%lld exceeds the 2^31 entries 32-bit list offsets can address",
                  (long long)R_cap);
   memset(out, 0, sizeof(*out));
   const size_t Pz = (size_t)P;
@@ -207,19 +197,15 @@ int skgs_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R_cap, skg
   out->point_offsets = take(Pz * 4);
   out->geom_grads = take(Pz * 48);
   out->geom_bytes = o;
-  // ---- binning: two physical key/value buffers; keys are emitted into a, the executed radix passes alternate
-  //      a -> b -> a ...; header.final_buf names the buffer that holds the sorted lists (data dependent: passes whose
-  //      digit is constant are skipped on the device)
+  // ---- binning: keys / values in emission order, the per-tile segments they are scattered into, and - after the
+  //      per-tile sort - the sorted lists (in keys / vals again); the tile grid and the cursors are reset by one memset
   o = 0;
   const size_t Rz = (size_t)R_cap;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  out->keys_a = take(Rz * 8);
-  out->vals_a = take(Rz * 4);
-  out->keys_b = take(Rz * 8);
-  out->vals_b = take(Rz * 4);
-  out->sort_hist = take(8 * 256 * sizeof(uint32_t));
-  out->sort_status = take(((Rz + OS_TILE_KEYS - 1) / OS_TILE_KEYS + 1) * 256 * sizeof(uint32_t));
-  out->tile_counts = take((size_t)(gx + 1) * (gy + 1) * sizeof(int32_t) * tile_cell_stride());
+  out->keys = take(Rz * 8);
+  out->vals = take(Rz * 4);
+  out->tile_pairs = take(Rz * 8);
+  out->tile_grid = take((size_t)(gx + 1) * (gy + 1) * sizeof(int32_t) * tile_cell_stride());
   out->tile_cursors = take((size_t)gx * gy * sizeof(uint32_t));
   out->binning_bytes = o;
   // ---- img
@@ -300,10 +286,7 @@ static int render_stage(const skgs_raster_settings* s, const RasterParams& rp, v
   rc = launch_binning(rp, (char*)geom, (char*)binning, (char*)img, lay, radii, R_cap, R_hint, emit, num_rendered_host,
                       st);
   if (rc) return rc;
-  if (!tile_sort_enabled() || rp.P == 0 || R_cap <= 0) {  // the tile-segmented binning plans the order itself
-    rc = launch_tile_order(rp, (char*)img, lay, st);
-    if (rc) return rc;
-  }
+
   if (s->debug & 2) return SKGS_OK;  // test hook: stop after binning
   return launch_composite_fwd(rp, (char*)geom, (char*)binning, (char*)img, lay, out_color, out_depth, out_alpha, st);
 }

@@ -177,8 +177,7 @@ int launch_deform_preprocess(const RasterParams& rp, const skgs_skeleton* sk, co
                              int32_t* radii, char* binning, char* img, int64_t R_cap, cudaStream_t st);
 int launch_fk_table(const skgs_skeleton* sk, float* sk_T, float* table, cudaStream_t st);
 int launch_tile_order(const RasterParams& rp, char* img, const skgs_raster_layout& lay, cudaStream_t st);
-// binning by tile-segmented sort (tile_sort.cu; default) or by the device-wide radix sort (SKGS_SORT=radix)
-bool tile_sort_enabled();
+// binning by tile-segmented sort (tile_sort.cu)
 int tile_cell_stride();
 int launch_tile_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                         int64_t R_cap, int64_t R_hint, cudaStream_t st);

@@ -212,7 +212,7 @@ __device__ __forceinline__ Item claim_item(uint32_t* ticket, uint32_t num_items,
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CW_THREADS)
 composite_fwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ order,
-                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ point_list,
                      const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
@@ -225,7 +225,6 @@ composite_fwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ 
   float4* cs = s_c[warp];
   pdl_wait();
   pdl_trigger();
-  const uint32_t* __restrict__ point_list = hdr->final_buf ? vals_b : vals_a;
   const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
   const size_t HW = (size_t)H * W;
   const uint32_t num_items = (uint32_t)tiles * ITEMS_PER_TILE;
@@ -414,7 +413,7 @@ __device__ __forceinline__ void flush_slots(float* part, const uint32_t* slot_id
 template <bool AUX>
 __global__ void __launch_bounds__(CW_THREADS, SKGS_BWD_MINBLOCKS)
 composite_bwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ order,
-                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ point_list,
                      const skgs_raster_header* __restrict__ hdr, GeomIn G, const float* __restrict__ bg,
                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
                      const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth,
@@ -438,7 +437,6 @@ composite_bwd_kernel(int W, int H, int gx, int tiles, const uint4* __restrict__ 
   float4* slot_abc = s_slot_abc[warp];
   pdl_wait();
   pdl_trigger();
-  const uint32_t* __restrict__ point_list = hdr->final_buf ? vals_b : vals_a;
   const float bg0 = bg ? bg[0] : 0.f, bg1 = bg ? bg[1] : 0.f, bg2 = bg ? bg[2] : 0.f;
   const size_t HW = (size_t)H * W;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
@@ -651,8 +649,7 @@ int launch_composite_fwd(const RasterParams& rp, char* geom, char* binning, char
     SKGS_CUDA(launch_pdl(composite_fwd_kernel, dim3(grid), dim3(CW_THREADS), cfg.dyn_smem, st, rp.W, rp.H, rp.gx, tiles,
                          reinterpret_cast<const uint4*>(img + lay.tile_order),
                          reinterpret_cast<uint32_t*>(img + lay.work_counters),
-                         reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
-                         reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals),
                          reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
                          out_color, out_depth, out_alpha, reinterpret_cast<uint32_t*>(img + lay.n_contrib),
                          reinterpret_cast<float*>(img + lay.final_T)));
@@ -682,8 +679,7 @@ int launch_composite_bwd(const RasterParams& rp, char* geom, const char* binning
     auto kern = aux ? composite_bwd_kernel<true> : composite_bwd_kernel<false>;
     SKGS_CUDA(launch_pdl(kern, dim3(grid), dim3(CW_THREADS), cfg[aux].dyn_smem, st, rp.W, rp.H, rp.gx, tiles,
                          reinterpret_cast<const uint4*>(img + lay.tile_order), counters + 1,
-                         reinterpret_cast<const uint32_t*>(binning + lay.vals_a),
-                         reinterpret_cast<const uint32_t*>(binning + lay.vals_b),
+                         reinterpret_cast<const uint32_t*>(binning + lay.vals),
                          reinterpret_cast<const skgs_raster_header*>(geom + lay.header), geom_in(geom, lay), rp.bg,
                          reinterpret_cast<const uint32_t*>(img + lay.n_contrib),
                          reinterpret_cast<const float*>(img + lay.final_T), dL_dcolor, dL_ddepth, dL_dalpha, ggrad,

@@ -33,12 +33,10 @@ __device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 // small helpers
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int PRE_THREADS = 256;
-constexpr int MAX_PASSES = 8;
 constexpr uint64_t SCAN_FLAG_AGG = 1ull << 62;
 constexpr uint64_t SCAN_FLAG_INC = 2ull << 62;
 constexpr uint64_t SCAN_VAL_MASK = (1ull << 62) - 1;
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr uint32_t RANGE_UNSET = 0xffffffffu;  // ranges[t].x before the last radix pass has seen tile t
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
   uint64_t v;
@@ -73,17 +71,12 @@ struct Emit {
 };
 
 struct BinningOut {            // where the emitting kernel writes; all NULL in the geometry-only variant
-  uint64_t* keys;              // buffer a
-  uint32_t* vals;
-  uint32_t* hist;              // [passes][256] (radix binning)
-  uint32_t* tile_counts;       // [(gy+1)][(gx+1)] 2-D difference grid of the tile rectangles (tile-segmented binning:
-                               // its prefix sum is the number of keys per tile); NULL selects the radix bookkeeping
-  uint2* ranges;               // [tiles] reset to (RANGE_UNSET, 0)
-  uint32_t* counters;          // [2] compositing work tickets, reset to 0
+  uint64_t* keys;              // (tile << 32 | depth bits) in emission order
+  uint32_t* vals;              // Gaussian ids
+  int* grid;                   // [(gy+1)][(gx+1)] x cell_stride: 2-D difference grid of the tile rectangles; its prefix
+                               // sum (tile_plan_kernel) is the number of keys per tile
   uint32_t R_cap;
-  int passes;
-  int tiles;
-  int cell_stride;             // ints between two cells of the difference grid
+  int cell_stride;             // ints between two cells (one 128-byte line per cell: same-line atomics serialise in L2)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -266,31 +259,25 @@ __device__ __forceinline__ Emit preprocess_gaussian(const RasterParams& rp, cons
 // ------------------------------------------------------------------------------------------------------------------
 // Warp-cooperative emission of (tile << 32 | depth bits, Gaussian id) for the 32 Gaussians of a warp.
 // The warp's output slots [wbase, wbase + wtotal) are consecutive: lane l writes slots l, l+32, ... (coalesced 8- and
-// 4-byte stores; the owner of a slot is found by a 5-step binary search over the warp's inclusive prefix).  The digit
-// histograms of the radix sort are accumulated on the way (reference: duplicateWithKeys,
-// gaussian_rasterizer_forward.cu:45-73, emission order y-major within the rect, Gaussians in index order).
+// 4-byte stores; the owner of a slot is found by a 5-step binary search over the warp's inclusive prefix).  Every
+// Gaussian also adds its tile rectangle to the difference grid the per-tile sort is planned from (reference:
+// duplicateWithKeys, gaussian_rasterizer_forward.cu:45-73, emission order y-major within the rect, Gaussians in index
+// order).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void emit_warp(int lane, const Emit& e, uint32_t id, uint32_t excl_in_warp, uint32_t wbase,
-                                          uint32_t wtotal, int gx, const BinningOut& b, uint32_t* s_hist,
-                                          skgs_raster_header* hdr) {
+                                          uint32_t wtotal, int gx, const BinningOut& b, skgs_raster_header* hdr) {
   if (wtotal == 0) return;
   if ((uint64_t)wbase + wtotal > (uint64_t)b.R_cap) {  // arena too small: flag, keep what fits out of bounds-safe
     if (lane == 0) hdr->overflow = 1;
   }
-  const bool by_tile = b.tile_counts != nullptr;
-  if (by_tile && e.cnt > 0) {
+  if (e.cnt > 0) {
     // +1 on the rectangle [x0, x0+w) x [y0, y0+h) as four corner updates: 4 atomics per Gaussian instead of one per
     // key, and a tile that thousands of Gaussians cover is not one hot address (their corners are spread out)
-    int* dg = reinterpret_cast<int*>(b.tile_counts);
     const int gs = gx + 1, h = (int)e.cnt / e.w, cs = b.cell_stride;
-    atomicAdd(&dg[(e.y0 * gs + e.x0) * cs], 1);
-    atomicAdd(&dg[(e.y0 * gs + e.x0 + e.w) * cs], -1);
-    atomicAdd(&dg[((e.y0 + h) * gs + e.x0) * cs], -1);
-    atomicAdd(&dg[((e.y0 + h) * gs + e.x0 + e.w) * cs], 1);
-  }
-  if (!by_tile && e.cnt > 0) {  // depth digits: the same for all of this Gaussian's keys
-#pragma unroll
-    for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((e.dbits >> (8 * p)) & 255u)], e.cnt);
+    atomicAdd(&b.grid[(e.y0 * gs + e.x0) * cs], 1);
+    atomicAdd(&b.grid[(e.y0 * gs + e.x0 + e.w) * cs], -1);
+    atomicAdd(&b.grid[((e.y0 + h) * gs + e.x0) * cs], -1);
+    atomicAdd(&b.grid[((e.y0 + h) * gs + e.x0 + e.w) * cs], 1);
   }
   const uint32_t incl = excl_in_warp + e.cnt;
   for (uint32_t s0 = 0; s0 < wtotal; s0 += 32) {
@@ -304,62 +291,16 @@ __device__ __forceinline__ void emit_warp(int lane, const Emit& e, uint32_t id, 
     const uint32_t g_excl = __shfl_sync(FULL, excl_in_warp, g);
     const int g_x0 = __shfl_sync(FULL, e.x0, g), g_y0 = __shfl_sync(FULL, e.y0, g), g_w = __shfl_sync(FULL, e.w, g);
     const uint32_t g_d = __shfl_sync(FULL, e.dbits, g), g_id = __shfl_sync(FULL, id, g);
-    const bool valid = s < wtotal;
-    uint32_t tile = 0;
-    if (valid) {
+    if (s < wtotal) {
       const uint32_t k = s - g_excl;
       const uint32_t row = k / (uint32_t)g_w;
-      tile = (uint32_t)((g_y0 + (int)row) * gx + g_x0 + (int)(k - row * (uint32_t)g_w));
+      const uint32_t tile = (uint32_t)((g_y0 + (int)row) * gx + g_x0 + (int)(k - row * (uint32_t)g_w));
       const uint32_t slot = wbase + s;
       if (slot < b.R_cap) {
         b.keys[slot] = ((uint64_t)tile << 32) | g_d;
         b.vals[slot] = g_id;
       }
     }
-    if (by_tile) continue;
-    // tile digits: neighbouring slots mostly share the high digit -> aggregate equal digits before the atomic
-    const uint32_t act = __ballot_sync(FULL, valid);
-    for (int p = 4; p < b.passes; p++) {
-      const uint32_t d = valid ? ((tile >> (8 * (p - 4))) & 255u) : 0xffffffffu;
-      const uint32_t m = __match_any_sync(FULL, d) & act;
-      if (valid && lane == __ffs(m) - 1) atomicAdd(&s_hist[p * 256 + d], (uint32_t)__popc(m));
-    }
-  }
-}
-
-// Flush the CTA's digit histograms; the LAST CTA of the emitting kernel to get here writes the plan of the radix
-// passes: a pass whose digit is identical for all n keys is skipped (never the last one, which also produces the tile
-// ranges), the others ping-pong a -> b -> a ...; final_buf = where the sorted lists end up.
-__device__ __forceinline__ void finish_emission(int tid, int nthreads, uint32_t* s_hist, const BinningOut& b,
-                                                skgs_raster_header* hdr, uint32_t num_ctas, uint32_t* s_flag) {
-  if (b.tile_counts != nullptr) return;  // tile-segmented binning: the per-tile counts are all the next stage needs
-  __syncthreads();
-  for (int k = tid; k < b.passes * 256; k += nthreads) {
-    const uint32_t c = s_hist[k];
-    if (c) atomicAdd(&b.hist[k], c);
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) *s_flag = (atomicAdd(&hdr->emit_done, 1u) == num_ctas - 1u) ? 1u : 0u;
-  __syncthreads();
-  if (*s_flag == 0u) return;
-  __threadfence();
-  const uint32_t R = ld_volatile_u32(&hdr->num_rendered);
-  const uint32_t n = min(R, b.R_cap);
-  uint32_t constant_mask = 0;  // bit p: pass p has one digit holding all n keys
-  for (int p = 0; p < b.passes; p++) {
-    bool full = false;
-    for (int d = tid; d < 256; d += nthreads) full |= (n > 0 && ld_volatile_u32(&b.hist[p * 256 + d]) == n);
-    if (__syncthreads_or(full)) constant_mask |= 1u << p;
-  }
-  if (tid == 0) {
-    uint32_t buf = 0;
-    for (int p = 0; p < b.passes; p++) {
-      const bool skip = ((constant_mask >> p) & 1u) && p != b.passes - 1;
-      hdr->sort_plan[p] = (skip ? 1u : 0u) | (buf << 1);
-      if (!skip) buf ^= 1u;
-    }
-    hdr->final_buf = buf;
   }
 }
 
@@ -369,8 +310,8 @@ __device__ __forceinline__ void finish_emission(int tid, int nthreads, uint32_t*
 // ------------------------------------------------------------------------------------------------------------------
 template <bool EMIT>
 __device__ __forceinline__ void scan_and_emit(const RasterParams& rp, const Emit& e, int i, int bid, int num_blocks,
-                                              uint32_t* s_warp_sum, uint32_t* s_excl_p, uint32_t* s_flag,
-                                              uint32_t* s_hist, uint32_t* __restrict__ tiles_touched,
+                                              uint32_t* s_warp_sum, uint32_t* s_excl_p,
+                                              uint32_t* __restrict__ tiles_touched,
                                               uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ scan_state,
                                               skgs_raster_header* __restrict__ hdr, const BinningOut& bo) {
   const int tid = threadIdx.x;
@@ -434,8 +375,7 @@ __device__ __forceinline__ void scan_and_emit(const RasterParams& rp, const Emit
   if (i < rp.P) point_offsets[i] = s_excl + warp_off + incl;
   if (EMIT) {
     const uint32_t wtotal = __shfl_sync(FULL, incl, 31);
-    emit_warp(lane, e, (uint32_t)i, incl - touched, s_excl + warp_off, wtotal, rp.gx, bo, s_hist, hdr);
-    finish_emission(tid, PRE_THREADS, s_hist, bo, hdr, (uint32_t)num_blocks, s_flag);
+    emit_warp(lane, e, (uint32_t)i, incl - touched, s_excl + warp_off, wtotal, rp.gx, bo, hdr);
   }
 }
 
@@ -453,9 +393,7 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
   __shared__ int s_bid;
   __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
   __shared__ uint32_t s_excl;
-  __shared__ uint32_t s_flag;
   __shared__ float s_V[16], s_P[16], s_cam[3];
-  __shared__ uint32_t s_hist[EMIT ? MAX_PASSES * 256 : 1];
   const int tid = threadIdx.x;
   pdl_wait();
   pdl_trigger();
@@ -466,17 +404,9 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
     s_P[tid] = rp.proj[tid];
   }
   if (tid < 3) s_cam[tid] = rp.campos[tid];
-  if (EMIT)
-    for (int k = tid; k < bo.passes * 256; k += PRE_THREADS) s_hist[k] = 0;
   __syncthreads();
   const int bid = s_bid;
   const int i = bid * PRE_THREADS + tid;
-  if (EMIT) {  // this CTA's share of the per-forward resets: tile ranges, compositing tickets
-    const int per = (bo.tiles + num_blocks - 1) / num_blocks;
-    for (int t = bid * per + tid; t < min(bo.tiles, (bid + 1) * per); t += PRE_THREADS)
-      bo.ranges[t] = make_uint2(RANGE_UNSET, 0u);
-    if (bid == 0 && tid < 2) bo.counters[tid] = 0u;
-  }
 
   Emit e;
   e.cnt = 0; e.x0 = 0; e.y0 = 0; e.w = 0; e.dbits = 0;
@@ -500,8 +430,8 @@ preprocess_scan_kernel(RasterParams rp, const float* __restrict__ means3D, const
                             cov3D_precomp ? cov3D_precomp + 6 * (size_t)i : nullptr, s0, s1, s2, qx, qy, qz, qr, shs,
                             colors_precomp, go);
   }
-  scan_and_emit<EMIT>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, &s_flag, s_hist, tiles_touched, point_offsets,
-                      scan_state, hdr, bo);
+  scan_and_emit<EMIT>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, tiles_touched, point_offsets, scan_state, hdr,
+                      bo);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -535,9 +465,7 @@ deform_preprocess_kernel(RasterParams rp, DeformIO io, const float* __restrict__
   __shared__ int s_bid;
   __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
   __shared__ uint32_t s_excl;
-  __shared__ uint32_t s_flag;
   __shared__ float s_V[16], s_P[16], s_cam[3];
-  __shared__ uint32_t s_hist[MAX_PASSES * 256];
   const int tid = threadIdx.x;
   pdl_wait();
   pdl_trigger();
@@ -547,18 +475,11 @@ deform_preprocess_kernel(RasterParams rp, DeformIO io, const float* __restrict__
     s_P[tid] = rp.proj[tid];
   }
   if (tid < 3) s_cam[tid] = rp.campos[tid];
-  for (int k = tid; k < bo.passes * 256; k += PRE_THREADS) s_hist[k] = 0;
   load_joint_table(s_table, io.table, io.M);
   __syncthreads();
   const JointTable jt = joint_table_view(s_table, io.M);
   const int bid = s_bid;
   const int i = bid * PRE_THREADS + tid;
-  {  // this CTA's share of the per-forward resets: tile ranges, compositing tickets
-    const int per = (bo.tiles + num_blocks - 1) / num_blocks;
-    for (int t = bid * per + tid; t < min(bo.tiles, (bid + 1) * per); t += PRE_THREADS)
-      bo.ranges[t] = make_uint2(RANGE_UNSET, 0u);
-    if (bid == 0 && tid < 2) bo.counters[tid] = 0u;
-  }
   Emit e;
   e.cnt = 0; e.x0 = 0; e.y0 = 0; e.w = 0; e.dbits = 0;
   if (i < rp.P) {
@@ -584,8 +505,8 @@ deform_preprocess_kernel(RasterParams rp, DeformIO io, const float* __restrict__
     e = preprocess_gaussian(rp, s_V, s_P, s_cam, i, a.px, a.py, a.pz, a.opacity, nullptr, rp.mod * a.sx, rp.mod * a.sy,
                             rp.mod * a.sz, a.qx, a.qy, a.qz, a.qw, shs, nullptr, go);
   }
-  scan_and_emit<true>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, &s_flag, s_hist, tiles_touched, point_offsets,
-                      scan_state, hdr, bo);
+  scan_and_emit<true>(rp, e, i, bid, num_blocks, s_warp_sum, &s_excl, tiles_touched, point_offsets, scan_state, hdr,
+                      bo);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -597,19 +518,9 @@ __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_keys_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const float2* __restrict__ means2D,
                       const float* __restrict__ depths, const uint32_t* __restrict__ point_offsets,
                       skgs_raster_header* __restrict__ hdr, BinningOut bo) {
-  __shared__ uint32_t s_hist[MAX_PASSES * 256];
-  __shared__ uint32_t s_flag;
   const int tid = threadIdx.x, lane = tid & 31;
   pdl_wait();
   pdl_trigger();
-  for (int k = tid; k < bo.passes * 256; k += DUP_THREADS) s_hist[k] = 0;
-  {
-    const int per = (bo.tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    for (int t = blockIdx.x * per + tid; t < min(bo.tiles, ((int)blockIdx.x + 1) * per); t += DUP_THREADS)
-      bo.ranges[t] = make_uint2(RANGE_UNSET, 0u);
-    if (blockIdx.x == 0 && tid < 2) bo.counters[tid] = 0u;
-  }
-  __syncthreads();
   const int i = blockIdx.x * DUP_THREADS + tid;
   Emit e;
   e.cnt = 0; e.x0 = 0; e.y0 = 0; e.w = 0; e.dbits = 0;
@@ -636,262 +547,7 @@ duplicate_keys_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, 
     if (lane >= o) incl_w += n;
   }
   const uint32_t wtotal = __shfl_sync(FULL, incl_w, 31);
-  emit_warp(lane, e, (uint32_t)i, incl_w - e.cnt, wbase, wtotal, gx, bo, s_hist, hdr);
-  finish_emission(tid, DUP_THREADS, s_hist, bo, hdr, gridDim.x, &s_flag);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// K3: onesweep radix pass (8-bit digit), stable.  Status word: [31:29] pass tag, [28:27] flag, [26:0] count.
-//   * a pass the plan marks as skipped returns at once (its digit is the same for every key: identity permutation);
-//   * chained scan with a WARP-PARALLEL look-back: warp w owns digits 32w..32w+31, lane l fetches the 128-byte status
-//     slab of predecessor tile-1-l (eight 16-byte volatile loads), the 32 x 32 words are transposed through shared
-//     memory and lane k walks the 32 predecessors of digit 32w+k: 32 predecessors per L2 round trip instead of one (with
-//     every CTA of a pass resident at once, a serial walk costs tiles/2 dependent round trips - 19 us of a 20 us pass);
-//   * the LAST pass also produces the tile ranges: inside a CTA the keys of one digit run are fully sorted, so tile
-//     boundaries are visible locally; the first / last entry of every (CTA, tile) run does an atomicMin / atomicMax on
-//     ranges[tile] (identifyTileRanges of the reference, gaussian_rasterizer_forward.cu:77-94, without a kernel).
-// ------------------------------------------------------------------------------------------------------------------
-#ifndef SKGS_OS_THREADS
-#define SKGS_OS_THREADS 512
-#endif
-#ifndef SKGS_OS_ITEMS
-#define SKGS_OS_ITEMS 12   // 512 x 12 = 6144 keys per CTA tile, 16 warps: every phase is latency bound, warps hide it
-#endif
-constexpr int OS_THREADS = SKGS_OS_THREADS;
-constexpr int OS_ITEMS = SKGS_OS_ITEMS;
-constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // keys per CTA tile
-constexpr int OS_WARPS = OS_THREADS / 32;
-constexpr int OS_DIGITS = 256;                  // threads 0..255 also own one digit each
-constexpr int OS_DWARPS = OS_DIGITS / 32;
-constexpr uint32_t OS_FLAG_AGG = 1u, OS_FLAG_INC = 2u;
-constexpr uint32_t OS_VAL_MASK = (1u << 27) - 1;
-static_assert(OS_THREADS >= OS_DIGITS && OS_THREADS % 32 == 0, "one thread per digit");
-static_assert(OS_TILE >= 2048, "api.cu sizes the look-back words for tiles of at least 2048 keys");
-static_assert(OS_TILE * 12 >= OS_DWARPS * 32 * 33 * 4, "the look-back slabs alias the key + value staging area");
-
-// debug: per-tile phase timestamps of one radix pass (tools/sort_trace.py)
-__device__ unsigned long long* g_os_trace = nullptr;
-__device__ __forceinline__ void os_trace(uint32_t tile, int phase) {
-  if (g_os_trace != nullptr && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_os_trace[(size_t)tile * 8 + phase] = t;
-  }
-}
-
-struct OnesweepSmem {
-  uint64_t keys[OS_TILE];   // reorder staging; during the look-back keys + vals hold OS_DWARPS slabs of 32 x 33 words
-  uint32_t vals[OS_TILE];
-  uint32_t whist[OS_WARPS][OS_DIGITS];
-  uint32_t texcl[OS_DIGITS];   // exclusive prefix of this tile's digit counts
-  uint32_t goff[OS_DIGITS];    // global output offset of digit d minus texcl[d]
-  uint32_t gbase[OS_DIGITS];   // exclusive prefix of the global digit histogram
-  uint32_t warp_tot[OS_DWARPS];
-  uint32_t tile;
-};
-
-// exclusive scan over the 256 digits, one value per thread of the first 8 warps (all threads must call: barriers)
-__device__ __forceinline__ uint32_t digit_exclusive_scan(uint32_t v, int tid, uint32_t* warp_tot) {
-  const int lane = tid & 31, warp = tid >> 5;
-  uint32_t incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (tid < OS_DIGITS && lane == 31) warp_tot[warp] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  if (tid < OS_DIGITS)
-    for (int w = 0; w < warp; w++) woff += warp_tot[w];
-  __syncthreads();
-  return woff + incl - v;
-}
-
-__global__ void __launch_bounds__(OS_THREADS)
-onesweep_pass_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint64_t* __restrict__ keys_b,
-                     uint32_t* __restrict__ vals_b, skgs_raster_header* __restrict__ hdr, uint32_t R_cap,
-                     const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, int pass, int is_last,
-                     uint2* __restrict__ ranges) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  OnesweepSmem& S = *reinterpret_cast<OnesweepSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool dthread = tid < OS_DIGITS;  // owns digit `tid`
-  pdl_wait();
-  pdl_trigger();
-  if (hdr->overflow) return;
-  const uint32_t plan = hdr->sort_plan[pass];
-  if (plan & 1u) return;  // constant digit: nothing to do, the next pass reads the same buffer
-  const bool from_b = (plan >> 1) & 1u;
-  const uint64_t* __restrict__ kin = from_b ? keys_b : keys_a;
-  const uint32_t* __restrict__ vin = from_b ? vals_b : vals_a;
-  uint64_t* __restrict__ kout = from_b ? keys_a : keys_b;
-  uint32_t* __restrict__ vout = from_b ? vals_a : vals_b;
-  const int shift = 8 * pass;
-  const uint32_t tag = (uint32_t)pass;
-  uint32_t* ticket = &hdr->sort_ticket[pass];
-  const uint32_t n = min(hdr->num_rendered, R_cap);
-  const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
-  const uint32_t lanemask_lt = (1u << lane) - 1u;
-
-  // exclusive scan of the global digit histogram
-  {
-    const uint32_t c = dthread ? hist[tid] : 0u;
-    const uint32_t ex = digit_exclusive_scan(c, tid, S.warp_tot);
-    if (dthread) S.gbase[tid] = ex;
-  }
-
-  while (true) {
-    if (tid == 0) S.tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = S.tile;
-    if (tile >= num_tiles) break;
-    const uint32_t base = tile * OS_TILE;
-    const uint32_t cnt = min((uint32_t)OS_TILE, n - base);
-    os_trace(tile, 0);
-
-    uint64_t key[OS_ITEMS];
-    uint32_t val[OS_ITEMS];
-    uint16_t pos[OS_ITEMS];
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-      const uint32_t idx = warp * (32 * OS_ITEMS) + i * 32 + lane;
-      key[i] = idx < cnt ? kin[base + idx] : ~0ull;
-    }
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {  // values travel with the keys: issued now, consumed after the look-back
-      const uint32_t idx = warp * (32 * OS_ITEMS) + i * 32 + lane;
-      val[i] = idx < cnt ? vin[base + idx] : 0u;
-    }
-    for (int k = tid; k < OS_WARPS * OS_DIGITS; k += OS_THREADS) (&S.whist[0][0])[k] = 0;
-    __syncthreads();
-    os_trace(tile, 1);
-    // ---- stable per-warp ranking (items are warp-striped: item-major, then lane)
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-      const uint32_t idx = warp * (32 * OS_ITEMS) + i * 32 + lane;
-      const bool valid = idx < cnt;
-      const uint32_t d = valid ? (uint32_t)((key[i] >> shift) & 255ull) : 0xffffffffu;
-      const uint32_t m = __match_any_sync(FULL, d);
-      const int leader = __ffs(m) - 1;
-      uint32_t old = 0;
-      if (valid && lane == leader) {
-        old = S.whist[warp][d];
-        S.whist[warp][d] = old + __popc(m);
-      }
-      old = __shfl_sync(FULL, old, leader);
-      pos[i] = (uint16_t)(old + __popc(m & lanemask_lt));
-      __syncwarp();
-    }
-    __syncthreads();
-    os_trace(tile, 2);
-    // ---- per digit: cross-warp exclusive prefix, tile totals, publish, look back
-    uint32_t total = 0;
-    const int d = tid;
-    uint32_t* my = status + (size_t)tile * OS_DIGITS + (dthread ? d : 0);
-    if (dthread) {
-#pragma unroll
-      for (int w = 0; w < OS_WARPS; w++) {
-        const uint32_t c = S.whist[w][d];
-        S.whist[w][d] = total;
-        total += c;
-      }
-      st_volatile_u32(my, (tag << 29) | ((tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG) << 27) | total);
-    }
-    {  // exclusive scan of totals over digits
-      const uint32_t ex = digit_exclusive_scan(total, tid, S.warp_tot);
-      if (dthread) S.texcl[d] = ex;
-    }
-    os_trace(tile, 3);
-    uint32_t excl = 0;
-    if (tile > 0 && dthread) {
-      // warp-parallel look-back: warp w (< 8) owns digits 32w .. 32w+31 (thread tid owns digit tid)
-      uint32_t* slab = reinterpret_cast<uint32_t*>(S.keys) + warp * (32 * 33);
-      const uint32_t sentinel = (tag << 29) | (OS_FLAG_INC << 27);  // "before tile 0": inclusive prefix 0
-      bool done = false;
-      int j0 = (int)tile - 1;
-      while (true) {
-        const int jj = j0 - lane;
-        uint32_t w[32];
-        if (jj >= 0) {
-          const uint4* row = reinterpret_cast<const uint4*>(status + (size_t)jj * OS_DIGITS + warp * 32);
-          bool ready;
-          do {
-            ready = true;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const uint4 v = ld_volatile_v4(row + q);
-              w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-            }
-            // [31:29] tag, [28:27] flag: ready <=> (w >> 27) is tag*4 + 1 (aggregate) or tag*4 + 2 (inclusive)
-#pragma unroll
-            for (int k = 0; k < 32; k++) ready &= ((w[k] >> 27) - (tag * 4u + 1u)) < 2u;
-          } while (!ready);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; k++) w[k] = sentinel;
-        }
-#pragma unroll
-        for (int k = 0; k < 32; k++) slab[lane * 33 + k] = w[k];
-        __syncwarp();
-        {  // lane k walks the 32 predecessors of its digit in order, branch-free: every read is in flight at once
-          uint32_t alive = done ? 0u : 1u;
-#pragma unroll
-          for (int l = 0; l < 32; l++) {
-            const uint32_t x = slab[l * 33 + lane];
-            excl += alive ? (x & OS_VAL_MASK) : 0u;
-            alive &= (((x >> 27) & 3u) == OS_FLAG_INC) ? 0u : 1u;
-          }
-          done = alive == 0u;
-        }
-        __syncwarp();
-        if (__all_sync(FULL, done)) break;
-        j0 -= 32;
-      }
-      st_volatile_u32(my, (tag << 29) | (OS_FLAG_INC << 27) | (excl + total));
-    }
-    if (dthread) S.goff[d] = S.gbase[d] + excl - S.texcl[d];
-    __syncthreads();  // look-back slabs (aliasing S.keys) are dead from here on
-    os_trace(tile, 4);
-    // ---- reorder through shared memory, then coalesced scatter
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-      const uint32_t idx = warp * (32 * OS_ITEMS) + i * 32 + lane;
-      if (idx < cnt) {
-        const uint32_t dd = (uint32_t)((key[i] >> shift) & 255ull);
-        const uint32_t p = S.texcl[dd] + S.whist[warp][dd] + pos[i];
-        S.keys[p] = key[i];
-        S.vals[p] = val[i];
-      }
-    }
-    __syncthreads();
-    // fixed trip count: the shared-memory reads of all of a thread's keys are in flight together
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-      const uint32_t k = tid + i * OS_THREADS;
-      key[i] = k < cnt ? S.keys[k] : 0ull;
-      val[i] = k < cnt ? S.vals[k] : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-      const uint32_t k = tid + i * OS_THREADS;
-      if (k < cnt) {
-        const uint64_t kk = key[i];
-        const uint32_t dd = (uint32_t)((kk >> shift) & 255ull);
-        const uint32_t o = S.goff[dd] + k;
-        kout[o] = kk;
-        vout[o] = val[i];
-        if (is_last) {
-          // inside one digit run of this CTA the keys are fully sorted and land on consecutive output slots
-          const uint32_t t = (uint32_t)(kk >> 32);
-          if (k == 0 || (uint32_t)(S.keys[k - 1] >> 32) != t) atomicMin(&ranges[t].x, o);
-          if (k + 1 == cnt || (uint32_t)(S.keys[k + 1] >> 32) != t) atomicMax(&ranges[t].y, o + 1u);
-        }
-      }
-    }
-    __syncthreads();
-    os_trace(tile, 5);
-  }
+  emit_warp(lane, e, (uint32_t)i, incl_w - e.cnt, wbase, wtotal, gx, bo, hdr);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -908,8 +564,6 @@ static int num_sms() {
   return g_num_sms;
 }
 
-int sort_passes(int gx, int gy) { return (32 + (int)higher_msb((uint32_t)(gx * gy)) + 7) / 8; }
-
 static GeomOut geom_out(char* geom, const skgs_raster_layout& lay, int32_t* radii) {
   GeomOut o;
   o.radii = radii;
@@ -923,20 +577,18 @@ static GeomOut geom_out(char* geom, const skgs_raster_layout& lay, int32_t* radi
   return o;
 }
 
-static int binning_out(const RasterParams& rp, char* binning, char* img, const skgs_raster_layout& lay, int64_t R_cap,
-                       BinningOut& b) {
-  b.passes = sort_passes(rp.gx, rp.gy);
-  SKGS_CHECK_ARG(b.passes <= MAX_PASSES, "tile grid too large for the 64-bit key layout");
-  b.keys = reinterpret_cast<uint64_t*>(binning + lay.keys_a);
-  b.vals = reinterpret_cast<uint32_t*>(binning + lay.vals_a);
-  b.hist = reinterpret_cast<uint32_t*>(binning + lay.sort_hist);
-  b.tile_counts = tile_sort_enabled() ? reinterpret_cast<uint32_t*>(binning + lay.tile_counts) : nullptr;
+static void binning_out(const RasterParams& rp, char* binning, const skgs_raster_layout& lay, int64_t R_cap,
+                        BinningOut& b) {
+  b.keys = reinterpret_cast<uint64_t*>(binning + lay.keys);
+  b.vals = reinterpret_cast<uint32_t*>(binning + lay.vals);
+  b.grid = reinterpret_cast<int*>(binning + lay.tile_grid);
   b.cell_stride = tile_cell_stride();
-  b.ranges = reinterpret_cast<uint2*>(img + lay.ranges);
-  b.counters = reinterpret_cast<uint32_t*>(img + lay.work_counters);
   b.R_cap = (uint32_t)R_cap;
-  b.tiles = rp.gx * rp.gy;
-  return SKGS_OK;
+}
+
+// the difference grid and the per-tile fill cursors (adjacent in the arena) start every forward at zero
+static cudaError_t reset_tile_counters(char* binning, const skgs_raster_layout& lay, cudaStream_t st) {
+  return cudaMemsetAsync(binning + lay.tile_grid, 0, lay.binning_bytes - lay.tile_grid, st);
 }
 
 // preprocess + scan; with a binning arena (binning != NULL, R_cap > 0) the keys are emitted by the same kernel
@@ -951,10 +603,8 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
   SKGS_CUDA(cudaMemsetAsync(geom + lay.header, 0, lay.means2D - lay.header, st));
   BinningOut bo = {};
   if (emit) {
-    int rc = binning_out(rp, binning, img, lay, R_cap, bo);
-    if (rc) return rc;
-    // digit histograms + look-back words of the radix passes (adjacent): one memset
-    SKGS_CUDA(cudaMemsetAsync(binning + lay.sort_hist, 0, lay.binning_bytes - lay.sort_hist, st));
+    binning_out(rp, binning, lay, R_cap, bo);
+    SKGS_CUDA(reset_tile_counters(binning, lay, st));
   }
   if (rp.P > 0) {
     ProfScope prof_("preprocess_scan_kernel", st);
@@ -972,9 +622,6 @@ int launch_preprocess_scan(const RasterParams& rp, const float* means3D, const f
                            colors_precomp, opacities, scales, rotations, cov3D_precomp, go, tt, po, ss, gg, hdr,
                            nblocks, bo));
     SKGS_CHECK_LAUNCH("preprocess_scan_kernel");
-  } else if (emit) {  // P == 0: no kernel ran, the consumers still expect initialised ranges / tickets
-    SKGS_CUDA(cudaMemsetAsync(img + lay.ranges, 0, (size_t)bo.tiles * sizeof(uint2), st));
-    SKGS_CUDA(cudaMemsetAsync(img + lay.work_counters, 0, 2 * sizeof(uint32_t), st));
   }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -993,9 +640,8 @@ int launch_deform_preprocess(const RasterParams& rp, const skgs_skeleton* sk, co
   SKGS_CHECK_ARG(binning != nullptr && R_cap > 0 && rp.P > 0, "fused forward needs P > 0 and a binning arena");
   SKGS_CUDA(cudaMemsetAsync(geom + lay.header, 0, lay.means2D - lay.header, st));
   BinningOut bo = {};
-  int rc = binning_out(rp, binning, img, lay, R_cap, bo);
-  if (rc) return rc;
-  SKGS_CUDA(cudaMemsetAsync(binning + lay.sort_hist, 0, lay.binning_bytes - lay.sort_hist, st));
+  binning_out(rp, binning, lay, R_cap, bo);
+  SKGS_CUDA(reset_tile_counters(binning, lay, st));
   DeformIO io;
   io.M = sk->M; io.mode = sk->mode; io.temperature = sk->temperature; io.table = table;
   io.xyz = xyz; io.scaling = scaling; io.rotation = rotation; io.opacity = opacity_logit; io.sp_W = sk->sp_W;
@@ -1031,24 +677,24 @@ int launch_deform_preprocess(const RasterParams& rp, const skgs_skeleton* sk, co
   return SKGS_OK;
 }
 
-// radix passes (+ key emission from the stored geometry when `emit`: the split API and the capacity-retry path)
+// binning: (key emission from the stored geometry when `emit`: the split API and the capacity-retry path, then) the
+// tile-segmented sort of tile_sort.cu, which also plans the work order of the compositing kernels
 int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                    const int32_t* radii, int64_t R_cap, int64_t R_hint, bool emit, uint32_t* num_rendered_host,
                    cudaStream_t st) {
   auto* hdr = reinterpret_cast<skgs_raster_header*>(geom + lay.header);
   const int tiles = rp.gx * rp.gy;
-  if (rp.P == 0 || R_cap <= 0) {
+  if (rp.P == 0 || R_cap <= 0) {  // nothing to bin: empty ranges, launch_tile_order builds the (all empty) schedule
     SKGS_CUDA(cudaMemsetAsync(img + lay.ranges, 0, (size_t)tiles * sizeof(uint2), st));
-    SKGS_CUDA(cudaMemsetAsync(img + lay.work_counters, 0, 2 * sizeof(uint32_t), st));
-    return SKGS_OK;
+    SKGS_CUDA(cudaMemsetAsync(img + lay.work_counters, 0, 8 * sizeof(uint32_t), st));
+    return launch_tile_order(rp, img, lay, st);
   }
-  BinningOut bo = {};
-  int rc = binning_out(rp, binning, img, lay, R_cap, bo);
-  if (rc) return rc;
   if (emit) {
-    // reset what a previous render stage on the same geometry may have left: overflow flag, tickets, plan, histograms
-    SKGS_CUDA(cudaMemsetAsync(&hdr->overflow, 0, sizeof(uint32_t) * (1 + 8 + 8 + 2), st));
-    SKGS_CUDA(cudaMemsetAsync(binning + lay.sort_hist, 0, lay.binning_bytes - lay.sort_hist, st));
+    BinningOut bo = {};
+    binning_out(rp, binning, lay, R_cap, bo);
+    // reset what a previous render stage on the same geometry may have left: the overflow flag, the tile counters
+    SKGS_CUDA(cudaMemsetAsync(&hdr->overflow, 0, sizeof(uint32_t), st));
+    SKGS_CUDA(reset_tile_counters(binning, lay, st));
     ProfScope prof_("duplicate_keys_kernel", st);
     SKGS_CUDA(launch_pdl(duplicate_keys_kernel, dim3((rp.P + DUP_THREADS - 1) / DUP_THREADS), dim3(DUP_THREADS), 0, st,
                          rp.P, rp.gx, rp.gy, radii, reinterpret_cast<const float2*>(geom + lay.means2D),
@@ -1058,41 +704,7 @@ int launch_binning(const RasterParams& rp, char* geom, char* binning, char* img,
   }
   if (num_rendered_host)
     SKGS_CUDA(cudaMemcpyAsync(num_rendered_host, hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (bo.tile_counts != nullptr) return launch_tile_binning(rp, geom, binning, img, lay, R_cap, R_hint, st);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SKGS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(OnesweepSmem)));
-    attr_set = true;
-  }
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, onesweep_pass_kernel, OS_THREADS, sizeof(OnesweepSmem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
-  const int64_t hint = R_hint > 0 ? (R_hint < R_cap ? R_hint : R_cap) : R_cap;
-  int grid = (int)((hint + OS_TILE - 1) / OS_TILE);
-  const int cap = ctas_per_sm * num_sms();
-  grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
-  uint32_t* status = reinterpret_cast<uint32_t*>(binning + lay.sort_status);
-  for (int p = 0; p < bo.passes; p++) {
-    static const char* kPassName[MAX_PASSES] = {"onesweep_pass0", "onesweep_pass1", "onesweep_pass2", "onesweep_pass3",
-                                                "onesweep_pass4", "onesweep_pass5", "onesweep_pass6", "onesweep_pass7"};
-    ProfScope prof_(kPassName[p], st);
-    SKGS_CUDA(launch_pdl(onesweep_pass_kernel, dim3(grid), dim3(OS_THREADS), sizeof(OnesweepSmem), st,
-                         reinterpret_cast<uint64_t*>(binning + lay.keys_a),
-                         reinterpret_cast<uint32_t*>(binning + lay.vals_a),
-                         reinterpret_cast<uint64_t*>(binning + lay.keys_b),
-                         reinterpret_cast<uint32_t*>(binning + lay.vals_b), hdr, (uint32_t)R_cap, bo.hist + p * 256,
-                         status, p, p == bo.passes - 1 ? 1 : 0, bo.ranges));
-    SKGS_CHECK_LAUNCH("onesweep_pass_kernel");
-  }
-  return SKGS_OK;
+  return launch_tile_binning(rp, geom, binning, img, lay, R_cap, R_hint, st);
 }
 
 }  // namespace skgs
-
-extern "C" __attribute__((visibility("default"))) void skgs_debug_set_sort_trace(void* p) {
-  unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
-  cudaMemcpyToSymbol(skgs::g_os_trace, &q, sizeof(q));
-}

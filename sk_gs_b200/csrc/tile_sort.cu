@@ -501,23 +501,21 @@ int sm_count() {
 
 }  // namespace
 
-size_t tile_count_cells(int gx, int gy) { return (size_t)(gx + 1) * (gy + 1); }
-
 // plan + scatter + per-tile sort; the keys / values were emitted into buffer a, the tile rectangles into the grid
 int launch_tile_binning(const RasterParams& rp, char* geom, char* binning, char* img, const skgs_raster_layout& lay,
                         int64_t R_cap, int64_t R_hint, cudaStream_t st) {
   auto* hdr = reinterpret_cast<skgs_raster_header*>(geom + lay.header);
   const int tiles = rp.gx * rp.gy;
-  auto* keys_a = reinterpret_cast<uint64_t*>(binning + lay.keys_a);
-  auto* vals_a = reinterpret_cast<uint32_t*>(binning + lay.vals_a);
-  auto* keys_b = reinterpret_cast<uint64_t*>(binning + lay.keys_b);
-  auto* grid_cells = reinterpret_cast<int*>(binning + lay.tile_counts);
+  auto* keys_a = reinterpret_cast<uint64_t*>(binning + lay.keys);
+  auto* vals_a = reinterpret_cast<uint32_t*>(binning + lay.vals);
+  auto* keys_b = reinterpret_cast<uint64_t*>(binning + lay.tile_pairs);
+  auto* grid_cells = reinterpret_cast<int*>(binning + lay.tile_grid);
   auto* cursors = reinterpret_cast<uint32_t*>(binning + lay.tile_cursors);
   auto* ranges = reinterpret_cast<uint2*>(img + lay.ranges);
   auto* order = reinterpret_cast<uint4*>(img + lay.tile_order);
   auto* counters = reinterpret_cast<uint32_t*>(img + lay.work_counters);
   {
-    const size_t cells = tile_count_cells(rp.gx, rp.gy);
+    const size_t cells = (size_t)(rp.gx + 1) * (rp.gy + 1);
     SKGS_CHECK_ARG(cells <= (size_t)TP_SMEM_CELLS || tile_cell_stride() == 1, "padded tile grid too large");
     const size_t smem = cells <= (size_t)TP_SMEM_CELLS ? cells * sizeof(int) : 0;
     ProfScope prof_("tile_plan_kernel", st);

@@ -122,12 +122,12 @@ class RasterState(NamedTuple):
         return _lib.RasterHeader.from_buffer_copy(raw)
 
     def sorted_lists(self):
-        """(keys uint64-as-int64 [R], point_list int32 [R]) sorted by (tile, depth): the binning buffer the last executed
-        radix pass wrote (header.final_buf; synchronises the device).  R = min(num_rendered, R_cap)."""
+        """(keys uint64-as-int64 [R], point_list int32 [R]) sorted by (tile, depth), as the per-tile sort left them in
+        layout.keys / layout.vals (synchronises the device).  R = min(num_rendered, R_cap)."""
         h = self.header()
         lay = self.layout
         R = min(int(h.num_rendered), int(self.R_cap))
-        ko, vo = (lay.keys_b, lay.vals_b) if h.final_buf else (lay.keys_a, lay.vals_a)
+        ko, vo = lay.keys, lay.vals
         keys = self.binning[ko:ko + 8 * R].view(torch.int64)
         vals = self.binning[vo:vo + 4 * R].view(torch.int32)
         return keys, vals

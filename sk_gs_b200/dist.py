@@ -105,13 +105,6 @@ class SymmGradArena(GradArena):
         self.flat = buf[:self.numel]
         self.multimem = bool(self.handle.multicast_ptr)
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        # control words of the synced kernel (skgs_multimem_allreduce_synced), one 16-byte block per channel
-        self._ctrl = torch.zeros(8, 4, dtype=torch.int32, device=device)
-        need = (self.SYNC_CHANNEL0 + 2 * self._ctrl.shape[0]) * self.world * 4
-        self.synced = self.multimem and int(getattr(self.handle, 'signal_pad_size', 0)) >= need and \
-            hasattr(self.handle, 'signal_pad_ptrs_dev')
-
-    SYNC_CHANNEL0 = 32  # signal-pad channels [32, 48) belong to the synced kernel (torch's own barriers use low ones)
 
     def allreduce(self, scale: float = 1.0, group=None, chunks: int = 1, async_op: bool = False):
         if not self.multimem:  # NCCL path of the base class, on the group this arena was built for
@@ -120,27 +113,6 @@ class SymmGradArena(GradArena):
             self.flat.mul_(scale)
         self.allreduce_range(0, self.flat_padded.numel())
         return []
-
-    def allreduce_range_synced(self, start: int, stop: int, slot: int = 0, exit_barrier: bool = True,
-                               max_blocks: int = 0):
-        """SUM over ranks of flat[start:stop] in ONE launch: the cross-GPU barriers before (all producers done) and after
-        (all slices reduced and broadcast) are part of the kernel (epoch flags through the signal pads over NVLink).
-        `slot` (0..7) selects the signal-pad channels + control words: calls that may be in flight at the same time (two
-        streams) need different slots.  `exit_barrier=False`: completion is covered by a later synced call that every
-        rank issues after joining this stream.  `max_blocks` caps the grid of a call that overlaps other kernels."""
-        from . import _lib
-        if not self.synced:
-            return self.allreduce_range(start, stop, channel=slot)
-        assert start % 4 == 0 and stop % 4 == 0 and 0 <= start <= stop <= self.flat_padded.numel()
-        st = torch.cuda.current_stream(self.flat.device).cuda_stream
-        _lib.check(_lib.lib().skgs_multimem_allreduce_synced(
-            self.handle.multicast_ptr + 4 * start, stop - start, self.rank, self.world, self.handle.signal_pad_ptrs_dev,
-            self.SYNC_CHANNEL0 + 2 * slot, self._ctrl[slot].data_ptr(), int(exit_barrier), int(max_blocks), st),
-            'skgs_multimem_allreduce_synced')
-
-    def sync_error(self) -> bool:
-        """Did a synced call give up waiting for a peer (results invalid)?  Synchronises the device."""
-        return bool(self._ctrl[:, 3].any().item())
 
     def allreduce_range(self, start: int, stop: int, channel: int = 0):
         """SUM over ranks of flat[start:stop] (both multiples of 4) on the CURRENT stream; `channel` selects the pair of

@@ -42,12 +42,12 @@ def test_layout_query_is_host_only_and_consistent():
     assert all(v % 256 == 0 for k, v in offs.items())
     assert offs['header'] == 0 and offs['scan_state'] > 0 and offs['means2D'] > offs['scan_state']
     assert lay.geom_bytes >= 100000 * (8 + 4 + 24 + 16 + 16 + 16 + 1 + 4 + 4 + 48)
-    assert lay.binning_bytes >= 1000000 * 24
+    assert lay.binning_bytes >= 1000000 * 20
     assert lay.img_bytes >= 2500 * 8 + 2 * 800 * 800 * 4
-    # two physical key / value buffers the radix passes ping-pong between (header.final_buf names the sorted one)
-    assert len({offs['keys_a'], offs['vals_a'], offs['keys_b'], offs['vals_b']}) == 4
-    assert offs['sort_hist'] > offs['vals_b'] and offs['sort_status'] > offs['sort_hist']
-    assert C.sizeof(_lib.RasterHeader) == 128 and _lib.RasterHeader.final_buf.offset == 80
+    # keys / values, the per-tile segments of the scatter pass, then the tile grid + cursors one memset resets
+    assert len({offs['keys'], offs['vals'], offs['tile_pairs']}) == 3
+    assert offs['tile_grid'] > offs['tile_pairs'] and offs['tile_cursors'] > offs['tile_grid']
+    assert C.sizeof(_lib.RasterHeader) == 128 and _lib.RasterHeader.overflow.offset == 12
 
 
 def test_errors_are_reported_not_swallowed():
@@ -55,8 +55,8 @@ def test_errors_are_reported_not_swallowed():
     lay = _lib.RasterLayout()
     assert L.skgs_raster_layout_query(-1, 800, 800, 0, C.byref(lay)) == -1
     assert b'bad sizes' in L.skgs_last_error()
-    assert L.skgs_raster_layout_query(10, 800, 800, 1 << 27, C.byref(lay)) == -1
-    assert b'2^27' in L.skgs_last_error()
+    assert L.skgs_raster_layout_query(10, 800, 800, 1 << 31, C.byref(lay)) == -1
+    assert b'2^31' in L.skgs_last_error()
     # NULL settings / skeleton are rejected before any CUDA call
     assert L.skgs_raster_forward_geometry(None, 0, 0, *([None] * 10), 0, *([None] * 3)) == -1
     assert b'settings is NULL' in L.skgs_last_error()
@@ -143,17 +143,18 @@ def test_widening_entry_points_validate_arguments_before_any_device_work():
 def test_sass_carries_the_instructions_the_design_relies_on():
     """Evidence that the shipped binary is the design DESIGN.md describes (no GPU needed, cuobjdump on the in-tree .so):
     NVLS in-switch reduction (multimem.ld_reduce -> LDGMC...ADD.F32x4, multimem.st -> STG.E.128.STRONG.SYS), one 16-byte
-    vector RED per gradient group in the compositing backward, match.any ranking in the onesweep sort, and nothing
+    vector RED per gradient group in the compositing backward, match.any ranking in the per-tile sort, and nothing
     compiled for an architecture other than sm_100a."""
     import subprocess
     sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert len(re.findall(r'LDGMC\.E\.ADD\.F32x4', sass)) >= 4            # allreduce_mm.cu
     assert 'STG.E.128.STRONG.SYS' in sass                                 # multimem.st of the reduced slice
     assert len(re.findall(r'REDG\.E\.ADD\.F32x4', sass)) >= 3             # composite.cu flush_slots: 3 x red.v4.f32
-    assert 'MATCH.ANY' in sass                                            # raster_fwd.cu onesweep ranking
+    assert 'MATCH.ANY' in sass                                            # tile_sort.cu radix ranking
     assert 'REDG.E.ADD.F64' in sass                                       # image_loss.cu loss sums
     funcs = set(re.findall(r'Function : (\S+)', sass))
-    for name in ('composite_fwd_kernel', 'composite_bwd_kernel', 'onesweep_pass_kernel', 'preprocess_scan_kernel',
+    for name in ('composite_fwd_kernel', 'composite_bwd_kernel', 'tile_plan_kernel', 'tile_scatter_kernel', 'tile_sort_kernel',
+                 'deform_preprocess_kernel', 'preprocess_scan_kernel', 'densify_apply_kernel', 'sp_table_kernel',
                  'lbs_fwd_kernel', 'fk_table_kernel', 'lbs_bwd_jm_kernel', 'multimem_allreduce_kernel', 'ssim_stats_kernel',
                  'ssim_grad_kernel', 'adam_kernel', 'small_gemm_kernel'):
         assert any(name in f for f in funcs), name
