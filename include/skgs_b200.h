@@ -181,7 +181,9 @@ SKGS_API int skgs_raster_backward(const skgs_raster_settings* s, int32_t P, int3
  * exp(_scaling), dL_drotation = normalize-backward at (_rotation + d_rot), dL_dopacity = dL/dopacity * s(1 - s) - and
  * dL/dscales, dL/drotations, dL/dopacity never touch HBM.  SH colours + scale / rotation inputs only (the SK_GS
  * training step); rotations (x,y,z,w).  The LBS backward then takes dL_dd_xyz = dL_dxyz, dL_dd_rot = dL_drotation,
- * dL_dd_scale.  d_rot may be NULL (static stage). */
+ * dL_dd_scale.  d_rot may be NULL (static stage).  dL_dd_xyz / dL_dd_rot (may be NULL): private copies of dL_dxyz /
+ * dL_drotation for a caller whose all-reduce overwrites those two (in an arena) while the LBS backward still needs the
+ * local values. */
 SKGS_API int skgs_raster_assemble_backward(const skgs_raster_settings* s, int32_t P, int32_t M, const float* means3D,
                                            const float* shs, const float* scales, const float* rotations,
                                            const int32_t* radii, void* geom, const void* binning, int64_t R_cap,
@@ -189,7 +191,8 @@ SKGS_API int skgs_raster_assemble_backward(const skgs_raster_settings* s, int32_
                                            const float* dL_dalpha, const float* scaling, const float* rotation,
                                            const float* opacity_logit, const float* d_rot, float* dL_dxyz,
                                            float* dL_dmeans2D, float* dL_dsh, float* dL_dscaling, float* dL_drotation,
-                                           float* dL_dopacity, float* dL_dd_scale, void* stream);
+                                           float* dL_dopacity, float* dL_dd_scale, float* dL_dd_xyz,
+                                           float* dL_dd_rot, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Skeleton forward kinematics + linear blend skinning (+ optional output assembly)

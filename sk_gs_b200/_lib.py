@@ -109,7 +109,7 @@ _SIGNATURES = {
     'skgs_raster_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 7 + [_vp, _vp, _i64, _vp] +
                              [_vp] * 12),
     'skgs_raster_assemble_backward': (C.c_int, [C.POINTER(RasterSettings), _i32, _i32] + [_vp] * 5 +
-                                      [_vp, _vp, _i64, _vp] + [_vp] * 3 + [_vp] * 4 + [_vp] * 7 + [_vp]),
+                                      [_vp, _vp, _i64, _vp] + [_vp] * 3 + [_vp] * 4 + [_vp] * 9 + [_vp]),
     'skgs_fk_lbs_forward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 9),
     'skgs_fk_lbs_workspace_bytes': (C.c_size_t, [_i32]),
     'skgs_fk_lbs_backward': (C.c_int, [C.POINTER(Skeleton), _i32] + [_vp] * 20),

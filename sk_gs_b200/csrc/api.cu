@@ -377,12 +377,12 @@ int skgs_raster_assemble_backward(const skgs_raster_settings* s, int32_t P, int3
                                   const float* scaling, const float* rotation, const float* opacity_logit,
                                   const float* d_rot, float* dL_dxyz, float* dL_dmeans2D, float* dL_dsh,
                                   float* dL_dscaling, float* dL_drotation, float* dL_dopacity, float* dL_dd_scale,
-                                  void* stream) {
+                                  float* dL_dd_xyz, float* dL_dd_rot, void* stream) {
   SKGS_CHECK_ARG(s != nullptr && s->quat_wxyz == 0, "the fused backward works on (x,y,z,w) rotations: quat_wxyz must be 0");
   SKGS_CHECK_ARG(shs && scales && rotations && scaling && rotation && opacity_logit, "NULL input");
   SKGS_CHECK_ARG(dL_dxyz && dL_dsh && dL_dscaling && dL_drotation && dL_dopacity && dL_dd_scale, "NULL output");
   const float* in[4] = {scaling, rotation, opacity_logit, d_rot};
-  float* out[4] = {dL_dscaling, dL_drotation, dL_dopacity, dL_dd_scale};
+  float* out[6] = {dL_dscaling, dL_drotation, dL_dopacity, dL_dd_scale, dL_dd_xyz, dL_dd_rot};
   return raster_backward_impl(s, P, M, means3D, shs, nullptr, scales, rotations, nullptr, radii, geom, binning, R_cap,
                               img, dL_dcolor, dL_ddepth, dL_dalpha, dL_dxyz, dL_dmeans2D, dL_dsh, nullptr, nullptr,
                               nullptr, nullptr, nullptr, in, out, stream);

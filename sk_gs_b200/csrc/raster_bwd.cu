@@ -30,8 +30,10 @@ constexpr int PB_THREADS = 256;
 struct AssembleBwd {
   const float *scaling, *rotation, *opacity, *d_rot;  // _scaling (log), _rotation (raw), _opacity (logit), LBS d_rot or NULL
   float *dscaling, *drotation, *dopacity;             // gradients of the canonical parameters
-  float* dd_scale;                                    // gradient of the LBS output d_scale (= dL/dscales); d_xyz and
-                                                      // d_rot share dL_dmeans3D / drotation
+  float* dd_scale;                                    // gradient of the LBS output d_scale (= dL/dscales)
+  float *dd_xyz, *dd_rot;                             // optional private copies of dL_dmeans3D / drotation (= dL/d_xyz,
+                                                      // dL/d_rot) for a caller that hands those two buffers to an
+                                                      // all-reduce while the LBS backward still reads them
 };
 
 __global__ void __launch_bounds__(PB_THREADS)
@@ -82,6 +84,7 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   }
   if (!vis) {
     dL_dmeans3D[3 * i] = dL_dmeans3D[3 * i + 1] = dL_dmeans3D[3 * i + 2] = 0.f;
+    if (ab.dd_xyz != nullptr) ab.dd_xyz[3 * i] = ab.dd_xyz[3 * i + 1] = ab.dd_xyz[3 * i + 2] = 0.f;
     if (dL_dcov3D)
       for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = 0.f;
     if (dL_dsh) {
@@ -97,6 +100,7 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
     if (ab.scaling != nullptr) {
       for (int k = 0; k < 3; k++) ab.dscaling[3 * i + k] = ab.dd_scale[3 * i + k] = 0.f;
       *reinterpret_cast<float4*>(ab.drotation + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ab.dd_rot != nullptr) *reinterpret_cast<float4*>(ab.dd_rot + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
       ab.dopacity[i] = 0.f;
     }
     return;
@@ -275,6 +279,11 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
   dL_dmeans3D[3 * i] = dmx;
   dL_dmeans3D[3 * i + 1] = dmy;
   dL_dmeans3D[3 * i + 2] = dmz;
+  if (ab.dd_xyz != nullptr) {
+    ab.dd_xyz[3 * i] = dmx;
+    ab.dd_xyz[3 * i + 1] = dmy;
+    ab.dd_xyz[3 * i + 2] = dmz;
+  }
   // ---- cov3D -> scale, rotation (:357-420)
   if (scales != nullptr && (dL_dscales != nullptr || ab.scaling != nullptr)) {
     float dsc[3];
@@ -350,6 +359,7 @@ preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const 
         go = make_float4(o.x * 1e12f, o.y * 1e12f, o.z * 1e12f, o.w * 1e12f);
       }
       *reinterpret_cast<float4*>(ab.drotation + 4 * i) = go;
+      if (ab.dd_rot != nullptr) *reinterpret_cast<float4*>(ab.dd_rot + 4 * i) = go;
       const float sg = 1.0f / (1.0f + expf(-ab.opacity[i]));
       ab.dopacity[i] = g[5] * sg * (1.0f - sg);
     }
@@ -368,6 +378,8 @@ int launch_preprocess_bwd(const RasterParams& rp, const float* means3D, const fl
     ab.scaling = assemble_in[0]; ab.rotation = assemble_in[1]; ab.opacity = assemble_in[2]; ab.d_rot = assemble_in[3];
     ab.dscaling = assemble_out[0]; ab.drotation = assemble_out[1]; ab.dopacity = assemble_out[2];
     ab.dd_scale = assemble_out[3];
+    ab.dd_xyz = assemble_out[4];
+    ab.dd_rot = assemble_out[5];
   }
   (void)colors_precomp;
   const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom + lay.cov3D);

@@ -312,10 +312,13 @@ def rasterize_backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=
 
 
 def rasterize_assemble_backward(state: RasterState, scaling, rotation, opacity_logit, d_rot, dL_dcolor, dL_ddepth=None,
-                                dL_dalpha=None, out=None, debug_flags: int = 0):
+                                dL_dalpha=None, out=None, debug_flags: int = 0, private_lbs_inputs: bool = False):
     """Rasterizer backward with the assembly backward fused into its per-Gaussian kernel
     (skgs_raster_assemble_backward).  Returns {'xyz' (= dL/dpoints = dL/d_xyz), 'means2D', 'shs', 'scaling', 'rotation'
-    (= dL/d_rot as well), 'opacity', 'dd_scale'}.  `out` may supply preallocated tensors (e.g. arena views)."""
+    (= dL/d_rot as well), 'opacity', 'dd_scale', 'dd_xyz', 'dd_rot'}.  `out` may supply preallocated tensors (e.g. arena
+    views).  'dd_xyz' / 'dd_rot' are what the LBS backward reads: the 'xyz' / 'rotation' tensors themselves, or - with
+    `private_lbs_inputs` - separate copies the kernel writes as well (needed when 'xyz' / 'rotation' live in an arena
+    whose all-reduce runs concurrently with the LBS backward)."""
     L = _lib.lib()
     (view, proj, campos, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp) = state.keep
     if shs is None or scales is None or rotations is None:
@@ -337,6 +340,8 @@ def rasterize_assemble_backward(state: RasterState, scaling, rotation, opacity_l
     g = {'xyz': pick('xyz', P, 3), 'means2D': pick('means2D', P, 3), 'shs': pick('shs', P, M, 3),
          'scaling': pick('scaling', P, 3), 'rotation': pick('rotation', P, 4), 'opacity': pick('opacity', P, 1),
          'dd_scale': pick('dd_scale', P, 3)}
+    g['dd_xyz'] = pick('dd_xyz', P, 3) if private_lbs_inputs else g['xyz']
+    g['dd_rot'] = pick('dd_rot', P, 4) if private_lbs_inputs else g['rotation']
     settings = state.settings
     if debug_flags:
         settings = _lib.RasterSettings.from_buffer_copy(bytes(state.settings))
@@ -349,7 +354,8 @@ def rasterize_assemble_backward(state: RasterState, scaling, rotation, opacity_l
             dL_dcolor.data_ptr(), _lib.ptr(dL_ddepth), _lib.ptr(dL_dalpha), scaling.data_ptr(), rotation.data_ptr(),
             opacity_logit.data_ptr(), _lib.ptr(d_rot), g['xyz'].data_ptr(), g['means2D'].data_ptr(),
             g['shs'].data_ptr(), g['scaling'].data_ptr(), g['rotation'].data_ptr(), g['opacity'].data_ptr(),
-            g['dd_scale'].data_ptr(), st), 'skgs_raster_assemble_backward')
+            g['dd_scale'].data_ptr(), g['dd_xyz'].data_ptr() if private_lbs_inputs else None,
+            g['dd_rot'].data_ptr() if private_lbs_inputs else None, st), 'skgs_raster_assemble_backward')
     return g
 
 

@@ -240,13 +240,16 @@ class HotPath:
             A = (lambda n: arena.view(n) if n in arena.offsets else None) if arena is not None else (lambda n: None)
             if fused:
                 scaling, rotation, opacity, d_rot = c2.keep
+                # mid_backward hands the rasterizer-side arena blocks ('xyz' and 'rotation' among them) to an all-reduce
+                # that runs WHILE the LBS backward reads dL/d_xyz and dL/d_rot: those two then need private copies
                 ga = DGR.rasterize_assemble_backward(
                     st, scaling, rotation, opacity, d_rot, dL_dimage,
                     out={'xyz': A('xyz'), 'means2D': A('viewspace_points'), 'shs': A('shs'), 'scaling': A('scaling'),
-                         'rotation': A('rotation'), 'opacity': A('opacity')})
+                         'rotation': A('rotation'), 'opacity': A('opacity')},
+                    private_lbs_inputs=mid_backward is not None and arena is not None)
                 g = {'means3D': ga['xyz'], 'means2D': ga['means2D'], 'shs': ga['shs']}
                 dscaling, drotation, dopacity = ga['scaling'], ga['rotation'], ga['opacity']
-                dd_xyz, dd_rot, dd_scale = ga['xyz'], ga['rotation'], ga['dd_scale']
+                dd_xyz, dd_rot, dd_scale = ga['dd_xyz'], ga['dd_rot'], ga['dd_scale']
             else:
                 g = DGR.rasterize_backward(st, dL_dimage, out={'means3D': A('xyz'), 'means2D': A('viewspace_points'),
                                                               'shs': A('shs')})
