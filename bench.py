@@ -204,7 +204,7 @@ class Runner:
 
     # ---- the one exchange step of a data-parallel iteration
     def exchange(self, out, grads):
-        if self.world == 1:
+        if self.world == 1 or os.environ.get('SKGS_BENCH_NO_EXCHANGE') == '1':  # diagnostic: view imbalance alone
             return
         a = self.arena
         if self.split_exchange:  # the rasterizer-side blocks were reduced under the LBS / FK backward (mid_backward)
@@ -225,9 +225,12 @@ class Runner:
         """Called when every rasterizer-side gradient (SH, means, scales, rotations, opacity: 92 % of the bytes) is
         final: their in-switch reduction runs on a side stream while the LBS and FK backward kernels execute."""
         main = torch.cuda.current_stream(self.dev)
+        if os.environ.get('SKGS_BENCH_NO_EXCHANGE') == '1':
+            return lambda: None
         self.side2.wait_stream(main)
         with torch.cuda.stream(self.side2):
-            self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0)
+            # no exit barrier: exchange() runs a full allreduce_range on every rank after the join below
+            self.arena.allreduce_range(0, self.arena.block_start('sp_W'), channel=0, exit_barrier=False)
         return lambda: main.wait_stream(self.side2)
 
     def capture(self, e2e: bool):

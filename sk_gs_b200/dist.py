@@ -114,9 +114,11 @@ class SymmGradArena(GradArena):
         self.allreduce_range(0, self.flat_padded.numel())
         return []
 
-    def allreduce_range(self, start: int, stop: int, channel: int = 0):
+    def allreduce_range(self, start: int, stop: int, channel: int = 0, exit_barrier: bool = True):
         """SUM over ranks of flat[start:stop] (both multiples of 4) on the CURRENT stream; `channel` selects the pair of
-        signal-pad barriers so that two ranges can be in flight on different streams."""
+        signal-pad barriers so that two ranges can be in flight on different streams.  `exit_barrier=False`: the caller
+        issues another allreduce_range (with both barriers) on every rank AFTER joining this stream - its entry barrier
+        is passed only when every rank's kernel of this call has completed, which is all the exit barrier guarantees."""
         from . import _lib
         if not self.multimem:
             dist.all_reduce(self.flat_padded[start:stop], group=self.group)
@@ -126,7 +128,8 @@ class SymmGradArena(GradArena):
         self.handle.barrier(channel=2 * channel)      # every rank's producers of this range have finished
         _lib.check(_lib.lib().skgs_multimem_allreduce(self.handle.multicast_ptr + 4 * start, stop - start, self.rank,
                                                       self.world, st), 'skgs_multimem_allreduce')
-        self.handle.barrier(channel=2 * channel + 1)  # every slice has been reduced and broadcast
+        if exit_barrier:
+            self.handle.barrier(channel=2 * channel + 1)  # every slice has been reduced and broadcast
 
     def block_start(self, name: str) -> int:
         return self.offsets[name][0]
