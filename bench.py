@@ -117,7 +117,14 @@ def algorithmic_bytes(P, M, K, C, R, W, H):
         'assemble_fwd_kernel': P * (44 + 40 + 44),
         'preprocess_scan_kernel': P * (44 + 12 * C + 75) + P * 8 + R * 12,  # + scan r/w + key emission
         'duplicate_keys_kernel': P * 8 + R * 12,
-        'onesweep_pass_kernel': R * 24,  # per executed pass: read key+value, write key+value
+        # fused per-Gaussian forward: canonical parameters + K sp_W gathers + SH in; assembled Gaussians, LBS outputs for
+        # the backward, geometry records (incl. the 16-byte culling record), scan words and the R keys / values out
+        'deform_preprocess_kernel': P * (44 + 4 * K + 12 * C) + P * (44 + 16 + 12 * K) + P * (75 + 16 + 8) + R * 12,
+        'fk_table_kernel': M * (44 + 28 + 96),
+        'tile_plan_kernel': (W // 16 + 1) * (H // 16 + 1) * 4 + (W // 16) * (H // 16) * 24,
+        'tile_scatter_kernel': R * (12 + 8),          # key + value in, (depth, id) word out
+        'tile_sort_kernel': R * (8 + 12),             # word in, sorted key + value out (both sort kernels together)
+        'tile_sort_large_kernel': 0,
         'composite_fwd_kernel': R * 44 + H * W * 28,
         'composite_bwd_kernel': R * (44 + 40) + H * W * (20 + 8),
         'preprocess_bwd_kernel': P * (44 + 12 * C + 75 + 40) + P * (12 + 12 + 16 + 4 + 12 + 12 * C),

@@ -123,11 +123,18 @@ tile_plan_kernel(int* __restrict__ grid, int gx, int gy, const skgs_raster_heade
   uint32_t run = incl - mine;
   for (int w = 0; w < warp; w++) run += s_wsum[w];
   const uint32_t run0 = run;
-  for (int t = t0; t < t1; t++) {
-    const uint32_t c = count_of(t);
-    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+  // every lane walks its `per` tiles in lock-step; equal length bins inside a warp (hundreds of empty tiles share bin
+  // 0) are aggregated before the shared-memory atomic
+  for (int j = 0; j < per; j++) {
+    const int t = t0 + j;
+    const bool valid = t < t1;
+    const uint32_t c = valid ? count_of(t) : 0u;
+    if (valid) ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
     run += c;
-    atomicAdd(&s_hist[length_bin(c)], 1u);
+    const int bin = valid ? length_bin(c) : -1;
+    const uint32_t m = __match_any_sync(FULLM, bin);
+    if (valid && lane == __ffs(m) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(m));
   }
   __syncthreads();
   // ---- descending exclusive prefix over the length bins (largest first)
@@ -149,10 +156,20 @@ tile_plan_kernel(int* __restrict__ grid, int gx, int gy, const skgs_raster_heade
   }
   __syncthreads();
   run = run0;
-  for (int t = t0; t < t1; t++) {
-    const uint32_t c = count_of(t);
-    const uint32_t p = atomicAdd(&s_base[length_bin(c)], 1u);
-    order[p] = c ? make_uint4((uint32_t)t, run, run + c, 0u) : make_uint4((uint32_t)t, 0u, 0u, 0u);
+  for (int j = 0; j < per; j++) {
+    const int t = t0 + j;
+    const bool valid = t < t1;
+    const uint32_t c = valid ? count_of(t) : 0u;
+    const int bin = valid ? length_bin(c) : -1;
+    const uint32_t m = __match_any_sync(FULLM, bin);
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(&s_base[bin], (uint32_t)__popc(m));
+    base = __shfl_sync(FULLM, base, leader);
+    if (valid) {
+      const uint32_t p = base + (uint32_t)__popc(m & lanemask_lt);
+      order[p] = c ? make_uint4((uint32_t)t, run, run + c, 0u) : make_uint4((uint32_t)t, 0u, 0u, 0u);
+    }
     run += c;
   }
   if (tid < 8) counters[tid] = tid == 3 ? s_nlarge : 0u;
@@ -194,9 +211,22 @@ tile_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
         rank[i] = s < n ? atomicAdd(&s_cnt[(uint32_t)(key[i] >> 32)], 1u) : 0u;
       }
       __syncthreads();
-      for (int t = tid; t < tiles; t += SC_THREADS) {
-        const uint32_t k = s_cnt[t];
-        if (k) s_cnt[t] = ranges[t].x + atomicAdd(&cursors[t], k);  // one reservation per (chunk, tile)
+      // one reservation per (chunk, tile); four tiles per thread and round so that the atomics' round trips overlap
+      for (int tb = tid; tb < tiles; tb += 4 * SC_THREADS) {
+        uint32_t k[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = tb + u * SC_THREADS;
+          k[u] = t < tiles ? s_cnt[t] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = tb + u * SC_THREADS;
+          b[u] = k[u] ? __ldg(&ranges[t].x) + atomicAdd(&cursors[t], k[u]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (k[u]) s_cnt[tb + u * SC_THREADS] = b[u];
       }
       __syncthreads();
 #pragma unroll
