@@ -364,10 +364,7 @@ def per_kernel_profile(hp, view, dL, flush, cfg, K_lbs):
     kern = {}
     for name, (n, us) in prof.items():
         per = us / n
-        key = 'onesweep_pass_kernel' if name.startswith('onesweep_pass') else name
-        gbs = ab.get(key, 0) / (per * 1e-6) / 1e9 if per > 0 else 0.0
-        if key == 'onesweep_pass_kernel' and per < 4.0:
-            gbs = 0.0  # a pass skipped on the device (constant digit) moves no bytes
+        gbs = ab.get(name, 0) / (per * 1e-6) / 1e9 if per > 0 else 0.0
         kern[name] = {'launches_per_step': n / nprof, 'us_per_launch': round(per, 3),
                       'us_per_step': round(us / nprof, 3), 'algorithmic_GBps': round(gbs, 1),
                       'frac_of_peak': round(gbs / peak, 4)}

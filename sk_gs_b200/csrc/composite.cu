@@ -4,11 +4,11 @@
 // 16x16 tile is latency / tail bound (42 % issue utilisation, SMs idle 40 % of the kernel because a few long tiles finish
 // last).  These kernels are WARP-granular and persistent:
 //   * work item  = 8 x 4 pixels of a tile (8 items per tile), one warp, ONE pixel per lane;
-//   * scheduling = a global ticket hands out work items in order of DEcreasing tile length (tile_order_kernel), so the
-//                  long tiles start first and the tail is made of short ones; no __syncthreads anywhere - a warp that
-//                  finishes (all its pixels saturated) immediately takes the next item; the ticket, tile id and range of
-//                  the NEXT item are fetched while the current one is composited (three dependent L2 round trips off
-//                  the critical path);
+//   * scheduling = a global ticket hands out work items in order of DEcreasing tile length (the order tile_plan_kernel
+//                  of tile_sort.cu writes: one 16-byte descriptor per tile = tile id + list range), so the long tiles
+//                  start first and the tail is made of short ones; no __syncthreads anywhere - a warp that finishes
+//                  (all its pixels saturated) immediately takes the next item (prefetching the next item's ticket was
+//                  measured and removed: profiles/r2_composite_notes.txt);
 //   * staging    = 32 Gaussians per batch in the warp's own shared-memory slice; the point_list index of batch b+2 and
 //                  the attributes of batch b+1 are in flight while batch b is composited;
 //   * culling    = phase 1 of every batch, lane j <-> staged Gaussian j: can any pixel centre of the 8x4 footprint reach
@@ -54,9 +54,9 @@ constexpr float PARKED = 1.0e18f;           // x coordinate of a finished pixel:
 constexpr uint32_t FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------------------------
-// tile order: tiles sorted by decreasing list length (coarse: 8 sub-steps per octave), one CTA.  Also turns the
-// (min, max) accumulators the last radix pass left in `ranges` into the reference's [start, end) / (0, 0) form and
-// resets the two compositing tickets.
+// tile order for a forward WITHOUT binning (P == 0 or no list capacity: every range is (0, 0), the image is the
+// background): tiles sorted by decreasing list length (coarse: 8 sub-steps per octave), one CTA; resets the compositing
+// tickets.  With binning the same order is produced by tile_plan_kernel (tile_sort.cu).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TO_THREADS = 1024;
 constexpr int TO_BINS = 8 * 33;

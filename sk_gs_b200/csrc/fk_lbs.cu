@@ -1,12 +1,15 @@
 // fk_lbs.cu - skeleton forward kinematics + linear blend skinning (+ output assembly) for sm_100a.
-//   fk_lbs_fwd_kernel : every CTA rebuilds the M joint transforms in shared memory (local transform, L pointer-jumping
-//                       rounds over the binary-lifting table, global transform) - M <= 1024 so this is cheaper than a
-//                       second launch - then streams Gaussians: brute-force K-nearest joints in registers, skinning
-//                       weights (4 modes), blend of mean / rotation / scale.  Joint table (t, R, dq, ds, pos) is read
-//                       from shared memory only; per-Gaussian traffic is one coalesced read of xyz (+K sp_W gathers)
-//                       and coalesced writes of the outputs.
-//   lbs_bwd_kernel    : per-Gaussian gradients, per-joint sums in shared memory, one global atomic set per CTA and joint
-//   fk_bwd_kernel     : single CTA, level-synchronous backward through the kinematic chain
+//   fk_table_kernel   : ONE CTA per call: the M joint transforms (local transform, L pointer-jumping rounds over the
+//                       binary-lifting table, global transform) in shared memory -> sk_T [M][7] and the joint table
+//                       (pos | t | R | d_rot | d_scale | aux, 24 floats per joint) the per-Gaussian kernels copy into
+//                       shared memory
+//   lbs_fwd_kernel    : streams Gaussians: brute-force K-nearest joints in registers, skinning weights (4 modes), blend
+//                       of mean / rotation / scale (deform.cuh, shared with the fused kernel of raster_fwd.cu)
+//   lbs_bwd_jm_kernel : per-Gaussian gradients staged per chunk, joint-major accumulation in registers (M <= 256), the
+//                       FK backward (level-synchronous sweep through the kinematic chain) in the last CTA to finish;
+//                       lbs_bwd_kernel (shared-memory atomics) + fk_bwd_kernel for more joints
+//   sp_table_kernel / sp_bwd_kernel : the sp-stage twin - the table comes from per-superpoint SE3 predicted by the
+//                       deformation network (networks/sk_gs.py:776-856)
 //   assemble_*        : the element-wise activations of networks/sk_gs.py:1192,1202-1203
 // Semantics: SURVEY.md App. A.1-A.3 (reference networks/sk_gs.py:193-206,751-774,1069-1150; lietorch algebra as in
 // my_ext/_C/include/lie.h:45-64,142-159,228-249).  Quaternions are (x,y,z,w).

@@ -1,13 +1,12 @@
-// raster_fwd.cu - forward half of the tile rasterizer for sm_100a:
-//   K1 preprocess_scan_kernel : projection, EWA cov2D, conic, radius, tile rect, SH->RGB, footprint-culling record
-//                               + fused decoupled-look-back prefix sum of tiles_touched (no scan kernel, no host sync
-//                               for R) + warp-cooperative emission of (tile << 32 | depth bits, id) with all radix digit
-//                               histograms + the plan of the radix passes (last CTA done)
-//   K2 duplicate_keys_kernel  : the same emission from stored geometry (split API / capacity retry only)
-//   K3 onesweep_pass_kernel   : one kernel per 8-bit digit, chained scan across key tiles with a warp-parallel
-//                               look-back, stable warp-level multi-split ranking (match.any), smem-staged coalesced
-//                               scatter; constant digits are skipped on the device; the last pass writes the tile ranges
-//   (tile order + compositing kernels live in composite.cu)
+// raster_fwd.cu - the per-Gaussian forward kernels of the tile rasterizer for sm_100a:
+//   preprocess_scan_kernel   : projection, EWA cov2D, conic, radius, tile rect, SH->RGB, footprint-culling record
+//                              + fused decoupled-look-back prefix sum of tiles_touched (no scan kernel, no host sync
+//                              for R) + (EMIT) warp-cooperative emission of (tile << 32 | depth bits, id) and the tile
+//                              rectangle of every Gaussian added to the difference grid the per-tile sort is planned from
+//   deform_preprocess_kernel : the same behind K-nearest-joint skinning + output assembly (deform.cuh): the whole
+//                              per-Gaussian forward of the SK_GS step in one kernel
+//   duplicate_keys_kernel    : the emission alone, from stored geometry (split API / capacity retry only)
+//   (binning continues in tile_sort.cu, compositing in composite.cu)
 // Semantics follow SURVEY.md App. A.4-A.6 (reference: my_ext/_C/src/nerf/gaussian_preprocess_colmap.cu:155-224,
 // gaussian_rasterizer_forward.cu:45-94,203-241, gaussian_render.cu:16-112).  This file MUST be compiled with
 // -fmad=false (and without fast-math): plain '*' and '+' below are separately rounded, exactly like the CPU oracle and

@@ -23,8 +23,8 @@ for _ in range(10): g.replay()
 a.record()
 for _ in range(100): g.replay()
 b.record(); torch.cuda.synchronize()
-sort = sum(v[1] for k, v in pr.items() if k.startswith('onesweep')) / 5
-print('%%-22s pdl=%%s graph %%.1f us | pre %%.1f sort %%.1f order %%.1f comp_fwd %%.1f comp_bwd %%.1f pre_bwd %%.1f' %% (os.environ.get('VNAME'), os.environ.get('SKGS_PDL', '1'), a.elapsed_time(b) * 10, (pr.get('preprocess_scan_kernel') or pr.get('deform_preprocess_kernel'))[1] / 5, sort, pr['tile_order_kernel'][1] / 5, pr['composite_fwd_kernel'][1] / 5, pr['composite_bwd_kernel'][1] / 5, pr['preprocess_bwd_kernel'][1] / 5))
+sort = sum(v[1] for k, v in pr.items() if k.startswith('tile_')) / 5
+print('%%-22s pdl=%%s graph %%.1f us | pre %%.1f binning %%.1f plan %%.1f comp_fwd %%.1f comp_bwd %%.1f pre_bwd %%.1f' %% (os.environ.get('VNAME'), os.environ.get('SKGS_PDL', '1'), a.elapsed_time(b) * 10, (pr.get('preprocess_scan_kernel') or pr.get('deform_preprocess_kernel'))[1] / 5, sort, pr['tile_plan_kernel'][1] / 5, pr['composite_fwd_kernel'][1] / 5, pr['composite_bwd_kernel'][1] / 5, pr['preprocess_bwd_kernel'][1] / 5))
 ''' % (ROOT, wl)
 libs = {os.path.basename(l)[8:-3]: l for l in sorted(glob.glob(os.path.join(ROOT, 'sk_gs_b200', 'variants', 'libskgs_*.so')))}
 runs = [(n, {}) for n in libs]

@@ -3,13 +3,13 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
-VARIANTS = {
+VARIANTS = {   # compile-time knobs that exist in csrc/ today (composite.cu, raster_fwd.cu)
     'base': [],
-    't256i24': ['-DSKGS_OS_THREADS=256', '-DSKGS_OS_ITEMS=24'],
-    't512i8': ['-DSKGS_OS_ITEMS=8'],
-    't512i16': ['-DSKGS_OS_ITEMS=16'],
-    't1024i6': ['-DSKGS_OS_THREADS=1024', '-DSKGS_OS_ITEMS=6'],
-    't1024i8': ['-DSKGS_OS_THREADS=1024', '-DSKGS_OS_ITEMS=8'],
+    'bwd_min4': ['-DSKGS_BWD_MINBLOCKS=4'],
+    'bwd_min6': ['-DSKGS_BWD_MINBLOCKS=6'],
+    'fwd_ilp2': ['-DSKGS_FWD_ILP2=1'],
+    'rslots8': ['-DSKGS_RSLOTS=8'],
+    'dp_min2': ['-DSKGS_DP_MINBLOCKS=2'],
 }
 out_dir = os.path.join(ROOT, 'sk_gs_b200', 'variants')
 os.makedirs(out_dir, exist_ok=True)
