@@ -21,7 +21,13 @@ constexpr int NGRAD = 12;  // packed per-Gaussian accumulators (composite.cu): m
 // ------------------------------------------------------------------------------------------------------------------
 // K7: preprocess backward
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PB_THREADS = 256;
+#ifndef SKGS_PB_THREADS
+#define SKGS_PB_THREADS 256
+#endif
+#ifndef SKGS_PB_MINBLOCKS
+#define SKGS_PB_MINBLOCKS 2   // 128 registers: two CTAs per SM (132 registers without the cap = one)
+#endif
+constexpr int PB_THREADS = SKGS_PB_THREADS;
 
 // Optional fusion of the assembly backward (networks/sk_gs.py:1192,1202-1203 + the activations of
 // networks/gaussian_splatting.py:155-160) into this kernel: with `scaling != NULL` the gradients of the assembled
@@ -36,7 +42,7 @@ struct AssembleBwd {
                                                       // all-reduce while the LBS backward still reads them
 };
 
-__global__ void __launch_bounds__(PB_THREADS)
+__global__ void __launch_bounds__(PB_THREADS, SKGS_PB_MINBLOCKS)
 preprocess_bwd_kernel(RasterParams rp, const float* __restrict__ means3D, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ cov3D_in, const int32_t* __restrict__ radii,

@@ -70,22 +70,25 @@ tile_plan_kernel(int* __restrict__ grid, int gx, int gy, const skgs_raster_heade
   // an overflowed emission left incomplete lists: hand out empty ranges (the image is invalid, the flag says so)
   const bool dead = hdr->overflow != 0;
   // ---- 2-D inclusive prefix of the difference grid: rows, then columns
-  int* G = (cells <= TP_SMEM_CELLS || cell_stride != 1) ? s_grid : grid;
-  if (G != grid)
+  // small grids are summed in shared memory, large ones in place in global memory (cell k lives at k * gstride)
+  const bool in_smem = cells <= TP_SMEM_CELLS;
+  int* G = in_smem ? s_grid : grid;
+  const int gstride = in_smem ? 1 : cell_stride;
+  if (in_smem)
     for (int k = tid; k < cells; k += TP_THREADS) G[k] = grid[(size_t)k * cell_stride];
   __syncthreads();
   for (int y = warp; y <= gy; y += TP_THREADS / 32) {  // rows: one warp per row, 32 cells per shuffle scan
     int carry = 0;
     for (int x0 = 0; x0 <= gx; x0 += 32) {
       const int x = x0 + lane;
-      int v = x <= gx ? G[y * gs + x] : 0;
+      int v = x <= gx ? G[(size_t)(y * gs + x) * gstride] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(FULLM, v, o);
         if (lane >= o) v += t;
       }
       v += carry;
-      if (x <= gx) G[y * gs + x] = v;
+      if (x <= gx) G[(size_t)(y * gs + x) * gstride] = v;
       carry = __shfl_sync(FULLM, v, 31);
     }
   }
@@ -94,14 +97,14 @@ tile_plan_kernel(int* __restrict__ grid, int gx, int gy, const skgs_raster_heade
     int carry = 0;
     for (int y0 = 0; y0 <= gy; y0 += 32) {
       const int y = y0 + lane;
-      int v = y <= gy ? G[y * gs + x] : 0;
+      int v = y <= gy ? G[(size_t)(y * gs + x) * gstride] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(FULLM, v, o);
         if (lane >= o) v += t;
       }
       v += carry;
-      if (y <= gy) G[y * gs + x] = v;
+      if (y <= gy) G[(size_t)(y * gs + x) * gstride] = v;
       carry = __shfl_sync(FULLM, v, 31);
     }
   }
@@ -109,7 +112,9 @@ tile_plan_kernel(int* __restrict__ grid, int gx, int gy, const skgs_raster_heade
   // ---- exclusive scan over the tiles: thread t owns `per` consecutive tiles
   const int per = (tiles + TP_THREADS - 1) / TP_THREADS;
   const int t0 = min(tiles, tid * per), t1 = min(tiles, t0 + per);
-  auto count_of = [&](int t) -> uint32_t { return dead ? 0u : (uint32_t)G[(t / gx) * gs + (t % gx)]; };
+  auto count_of = [&](int t) -> uint32_t {
+    return dead ? 0u : (uint32_t)G[(size_t)((t / gx) * gs + (t % gx)) * gstride];
+  };
   uint32_t mine = 0;
   for (int t = t0; t < t1; t++) mine += count_of(t);
   uint32_t incl = mine;
@@ -546,7 +551,6 @@ int launch_tile_binning(const RasterParams& rp, char* geom, char* binning, char*
   auto* counters = reinterpret_cast<uint32_t*>(img + lay.work_counters);
   {
     const size_t cells = (size_t)(rp.gx + 1) * (rp.gy + 1);
-    SKGS_CHECK_ARG(cells <= (size_t)TP_SMEM_CELLS || tile_cell_stride() == 1, "padded tile grid too large");
     const size_t smem = cells <= (size_t)TP_SMEM_CELLS ? cells * sizeof(int) : 0;
     ProfScope prof_("tile_plan_kernel", st);
     SKGS_CUDA(launch_pdl(tile_plan_kernel, dim3(1), dim3(TP_THREADS), smem, st, grid_cells, rp.gx, rp.gy,

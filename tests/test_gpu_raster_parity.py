@@ -142,6 +142,29 @@ def test_sort_long_tiles_and_depth_ties(P, longest):
         assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
 
 
+def test_large_tile_grid_paths():
+    """2560 x 1440 = 160 x 90 = 14 400 tiles: more than the shared-memory capacity of the plan kernel (the difference
+    grid is summed in place in global memory) and of the scatter kernel's per-chunk tile counters (one atomic per
+    entry): keys, point_list, ranges and the image are still bit-identical to the oracle."""
+    sc = S.make_scene('c1', P=20000, seed=23)
+    cam = sc.cameras[0]
+    cam.W, cam.H = 2560, 1440
+    cam.tanfovy = cam.tanfovx * cam.H / cam.W
+    net, _, _ = oracle_deform(sc)
+    net = {k: v.detach() for k, v in net.items()}
+    _, img, g, b = _oracle_forward(sc, net)
+    assert b.ranges.shape[0] == 160 * 90
+    for _ in range(2):  # split path, then keys emitted by the preprocess kernel
+        color, _, _, _, st = _gpu_forward(sc, net)
+        keys, plist = _sorted(st)
+        lay = st.layout
+        tiles = b.ranges.shape[0]
+        ranges = arena_view(st.img, lay.ranges, torch.int32, 2 * tiles).view(tiles, 2).cpu().numpy().view(np.uint32)
+        assert np.array_equal(keys, b.keys) and np.array_equal(plist, b.point_list)
+        assert np.array_equal(ranges, b.ranges)
+        assert np.array_equal(color.cpu().numpy().view(np.uint32), img.color.view(np.uint32))
+
+
 @pytest.mark.parametrize('name,P,seed', CASES)
 def test_composite_forward(name, P, seed):
     sc, net = _inputs(name, P, seed=seed)

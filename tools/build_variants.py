@@ -3,13 +3,15 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
-VARIANTS = {   # compile-time knobs that exist in csrc/ today (composite.cu, raster_fwd.cu)
+VARIANTS = {   # compile-time knobs that exist in csrc/ today
     'base': [],
-    'bwd_min4': ['-DSKGS_BWD_MINBLOCKS=4'],
-    'bwd_min6': ['-DSKGS_BWD_MINBLOCKS=6'],
-    'fwd_ilp2': ['-DSKGS_FWD_ILP2=1'],
-    'rslots8': ['-DSKGS_RSLOTS=8'],
-    'dp_min2': ['-DSKGS_DP_MINBLOCKS=2'],
+    'pb256x2': ['-DSKGS_PB_THREADS=256', '-DSKGS_PB_MINBLOCKS=2'],
+    'pb128x4': ['-DSKGS_PB_THREADS=128', '-DSKGS_PB_MINBLOCKS=4'],
+    'pb128x5': ['-DSKGS_PB_THREADS=128', '-DSKGS_PB_MINBLOCKS=5'],
+    'pb128x6': ['-DSKGS_PB_THREADS=128', '-DSKGS_PB_MINBLOCKS=6'],
+    'pb256x3': ['-DSKGS_PB_THREADS=256', '-DSKGS_PB_MINBLOCKS=3'],
+    'pb64x10': ['-DSKGS_PB_THREADS=64', '-DSKGS_PB_MINBLOCKS=10'],
+    'pb64x12': ['-DSKGS_PB_THREADS=64', '-DSKGS_PB_MINBLOCKS=12'],
 }
 out_dir = os.path.join(ROOT, 'sk_gs_b200', 'variants')
 os.makedirs(out_dir, exist_ok=True)
