@@ -154,3 +154,34 @@ def test_train_loop_keeps_training_across_densification():
         assert not hp.overflowed()
     assert results['graph'][1] == results['eager'][1]
     assert np.abs(np.array(results['graph'][0]) - np.array(results['eager'][0])).max() <= 1e-4
+
+
+def test_edge_cases_nothing_selected_everything_pruned_single_gaussian():
+    """Degenerate plans: no Gaussian qualifies (identity), every Gaussian is pruned (empty set), P = 1."""
+    g = torch.Generator().manual_seed(2)
+    for P in (1, 777):
+        params = dict(xyz=torch.randn(P, 3, generator=g), shs=torch.randn(P, 16, 3, generator=g),
+                      scaling=torch.full((P, 3), -4.0), rotation=torch.randn(P, 4, generator=g),
+                      opacity=torch.full((P, 1), 2.0))
+        t = {n: (p.to(DEV), torch.ones_like(p).to(DEV), torch.ones_like(p).to(DEV)) for n, p in params.items()}
+        stats = DensifyStats(P, DEV)  # denom = 0 -> NaN gradient -> 0: nothing is hot
+        res = densify_and_prune(t, stats, True, True, grad_threshold=0.0002, densify_extent=0.02, min_opacity=0.005,
+                                max_screen_size=20.0, prune_extent=0.2)
+        assert res.counts == dict(n_keep=P, n_clone=0, n_split=0, n_selected=0, n_new=P)
+        for n in t:
+            assert all(torch.equal(a, b) for a, b in zip(res.tensors[n], t[n])), n
+        assert torch.equal(res.src.cpu(), torch.arange(P, dtype=torch.int32))
+        # opacity below the threshold everywhere: the set becomes empty
+        t['opacity'] = (torch.full((P, 1), -20.0, device=DEV), t['opacity'][1], t['opacity'][2])
+        res = densify_and_prune(t, stats, False, True, min_opacity=0.005)
+        assert res.counts['n_new'] == 0 and res.tensors['xyz'][0].shape == (0, 3) and res.stats.P == 0
+    # statistics: invisible Gaussians (radii == 0) are left alone
+    stats = DensifyStats(5, DEV)
+    add_densification_stats(stats, torch.tensor([0, 3, 0, 7, 0], dtype=torch.int32, device=DEV),
+                            torch.tensor([[3.0, 4.0, 9.0]] * 5, device=DEV))
+    assert stats.denom.tolist() == [0, 1, 0, 1, 0] and stats.max_radii2D.tolist() == [0, 3, 0, 7, 0]
+    assert stats.grad_accum.tolist() == [0, 5, 0, 5, 0]
+    with pytest.raises(RuntimeError):
+        add_densification_stats(stats, torch.zeros(5, dtype=torch.int64, device=DEV), torch.zeros(5, 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        densify_and_prune({'xyz': (torch.zeros(4, 3, device=DEV), None, None)}, DensifyStats(4, DEV), True, True)

@@ -137,3 +137,20 @@ def test_argument_errors_are_loud():
         sp_warp(points, lv['sp_points'], lv['sp_t'], lv['raw_r'], K=9, mode='dist')
     with pytest.raises(RuntimeError):
         sp_warp(points.cpu(), lv['sp_points'].cpu(), lv['sp_t'].cpu(), lv['raw_r'].cpu(), K=2, mode='dist')
+
+
+def test_edge_cases_single_superpoint_and_empty_point_set():
+    """M = K = 1 (every Gaussian follows the one transform with weight 1) and P = 0."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randn(50, 3, generator=g).to(dev)
+    c, t = torch.randn(1, 3, generator=g).to(dev), torch.randn(1, 3, generator=g).to(dev)
+    q = torch.nn.functional.normalize(torch.randn(1, 4, generator=g), dim=-1).to(dev)
+    for method in ('LBS', 'LBS_c', 'largest'):
+        d_points, d_rot, d_scales, spT, w, idx = sp_warp(pts, c, t, q, None, None, K=1, mode='dist', method=method)
+        ref = OF.sp_stage(pts.double(), c.double(), t.double(), q.double(), None, None, K=1, mode='dist', method=method)
+        assert d_scales is None and torch.all(idx == 0) and torch.all(w == 1)
+        assert float((d_points.double() - ref[0]).abs().max()) <= 2e-6
+        assert float((d_rot - q.expand(50, 4)).abs().max()) <= 1e-7
+    out = sp_warp(pts[:0], c, t, q, None, None, K=1, mode='dist')
+    assert out[0].shape == (0, 3) and out[4].shape == (0, 1) and out[3].shape == (1, 7)

@@ -27,7 +27,7 @@ side = torch.cuda.Stream(dev)
 main = torch.cuda.current_stream(dev)
 side.wait_stream(main)
 with torch.cuda.stream(side):
-    a.allreduce_range(0, split, channel=0)
+    a.allreduce_range(0, split, channel=0, exit_barrier=False)  # covered by the second range's barriers (after the join)
 a.flat[split:].mul_(1.0)  # something on the main stream meanwhile
 main.wait_stream(side)
 a.allreduce_range(split, a.flat_padded.numel(), channel=1)
