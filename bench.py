@@ -41,6 +41,43 @@ import torch  # noqa: E402
 METRIC = 'train_steps_per_sec (FK+LBS+render fwd+bwd, one 800x800 view per step)'
 
 
+# what the watchdog needs: the section in progress and, once it exists, the headline line
+_STATE = {'section': 'setup', 'line': None, 'done': False}
+
+
+def _start_watchdog(seconds: float, rank: int):
+    """A benchmark must never hang the box (a collective that dead-locks spins on the GPU for ever): after `seconds`
+    the process prints what it has - the headline line if it was measured, marked `aborted` - and exits.  Every rank
+    runs its own watchdog, so torchrun sees all of them leave."""
+    import threading
+    import time
+
+    def run():
+        time.sleep(seconds)
+        if _STATE['done']:
+            return
+        line = _STATE['line']
+        if rank == 0:
+            if line is not None:
+                line = dict(line)
+                line['aborted'] = {'after_seconds': seconds, 'section': _STATE['section']}
+                print(json.dumps(line), flush=True)
+            else:
+                print(json.dumps({'error': f'watchdog: no headline after {seconds} s (in {_STATE["section"]})'}),
+                      flush=True)
+        sys.stdout.flush()
+        os._exit(0 if line is not None else 124)
+
+    threading.Thread(target=run, daemon=True).start()
+
+
+def shards_evenly(views_total, world: int) -> bool:
+    """Can this workload run on `world` ranks?  Weak scaling (views_total None: one view per rank) always; a fixed
+    number of views per step only when every rank gets the same number (a rank with fewer views - or none - would have
+    to mirror the other ranks' exchanges one for one, including those of their capture warm-up)."""
+    return views_total is None or (views_total >= world and views_total % world == 0)
+
+
 def _dist():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -164,6 +201,10 @@ class Runner:
         cfg = self.cfg = S.CONFIGS[name]
         self.strong = views_total is not None          # a fixed number of views per step, sharded over the ranks
         V = views_total if self.strong else world      # weak scaling: one view per rank
+        if V % world != 0:
+            # a rank without views (or with fewer than the others) would have to mirror the exchanges of the other ranks'
+            # capture warm-up one for one - not supported: fail on every rank alike instead of dead-locking a barrier
+            raise RuntimeError(f'{name}: {V} views per step cannot be sharded evenly over {world} ranks')
         self.V = V
         sc = self.sc = S.make_scene(cfg, views=V)
         self.my_views = shard_views(V, world, rank) if self.strong else [rank]
@@ -201,8 +242,8 @@ class Runner:
             self.arena = GradArena(shapes, dev, order=list(shapes))
         if multi_view:
             self.scratch = GradArena(shapes, dev, order=list(shapes))
-        self.split_exchange = world > 1 and getattr(self.arena, 'multimem', False) and len(self.my_views) == 1 \
-            and not self.strong
+        # one view on every rank (weak scaling, or V == world): the exchange is split and overlapped as in the headline
+        self.split_exchange = world > 1 and getattr(self.arena, 'multimem', False) and V == world
         self.side = torch.cuda.Stream(dev) if world > 1 else None
         self.side2 = torch.cuda.Stream(dev) if self.split_exchange else None
         self.graphs = {}
@@ -388,10 +429,13 @@ def run_ours(args, world, rank, local):
     run = Runner(args, name, world, rank, dev, views_total=strong_views)
     if rank == 0:
         sampler.start()
+    _STATE['section'] = 'headline'
     ms_dev = run.timed(False, K, args.warmup, flush)
     clocks = sampler.stop() if rank == 0 else None
     launches = K * getattr(run, 'launches', 0)
+    _STATE['section'] = 'e2e'
     ms_e2e = run.timed(True, K, max(args.warmup, 3), flush)
+    _STATE['section'] = 'exchange self-check'
     check = run.exchange_selfcheck()
     per_step_units = 1 if run.strong else run.V  # weak scaling: every rank's view is one step of the metric
     line = {
@@ -411,6 +455,7 @@ def run_ours(args, world, rank, local):
     }
     if check is not None:
         line['exchange_check'] = check
+    _STATE['line'], _STATE['section'] = line, 'per-kernel profile'
 
     extra_ok = not args.headline_only
     # ---- per-kernel table + roofline (rank 0, eager pass with events around every launch)
@@ -463,6 +508,10 @@ def run_ours(args, world, rank, local):
     if extra_ok and not args.no_workloads and name == 'c2':
         wl = {}
         for wname, views_total in (('ns', None), ('c3', 8), ('c4', 4)):
+            if not shards_evenly(views_total, world):
+                wl[wname] = {'skipped': f'{views_total} views per step do not shard evenly over {world} ranks'}
+                continue
+            _STATE['section'] = f'workload {wname}'
             try:
                 wl[wname] = secondary_workload(args, wname, views_total, world, rank, dev, flush)
             except Exception as e:  # noqa
@@ -470,6 +519,7 @@ def run_ours(args, world, rank, local):
                 if world > 1:
                     raise  # a rank that drops out of a collective would hang the others
             torch.cuda.empty_cache()
+        _STATE['section'] = 'workload c5'
         try:
             wl['c5'] = c5_fps(args, world, rank, dev, flush)
         except Exception as e:  # noqa
@@ -1020,6 +1070,8 @@ def main():
     ap.add_argument('--no-iteration', action='store_true', help='skip the MLP+loss+Adam full-iteration section')
     ap.add_argument('--no-workloads', action='store_true', help='skip the ns / c3 / c4 / c5 section')
     ap.add_argument('--headline-only', action='store_true', help='only value / e2e / kernels (quick runs)')
+    ap.add_argument('--watchdog', type=float, default=600.0,
+                    help='seconds after which a run that has not finished prints what it has and exits (0: off)')
     ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
                     help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
     args = ap.parse_args()
@@ -1039,8 +1091,11 @@ def main():
         os.environ.setdefault('MASTER_PORT', '29511')
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if args.watchdog > 0:
+        _start_watchdog(args.watchdog, rank)
     try:
         run_ours(args, world, rank, local)
+        _STATE['done'] = True
     finally:
         if world > 1:
             import torch.distributed as dist

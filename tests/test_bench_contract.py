@@ -37,3 +37,26 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0  # no CPU fallback of the product path
     assert not [l for l in out.stdout.splitlines() if l.startswith('{') and '"value"' in l]
+
+
+def test_fixed_view_workloads_run_only_where_they_shard_evenly():
+    """c3 (8 views per step) runs on 1, 2, 4 and 8 ranks; c4 (4 views) on 1, 2 and 4 - on 8 ranks it is skipped instead
+    of leaving four ranks without work inside a collective (which dead-locked a round-2 run)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert [n for n in (1, 2, 4, 8) if bench.shards_evenly(8, n)] == [1, 2, 4, 8]
+    assert [n for n in (1, 2, 3, 4, 8) if bench.shards_evenly(4, n)] == [1, 2, 4]
+    assert all(bench.shards_evenly(None, n) for n in (1, 2, 3, 8))
+
+
+def test_watchdog_prints_what_it_has_and_exits():
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; "
+            "bench._STATE['line'] = {'metric': 'm', 'value': 1.0}; bench._STATE['section'] = 'workload c4'; "
+            "bench._start_watchdog(0.3, 0); time.sleep(30)") % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert d['value'] == 1.0 and d['aborted']['section'] == 'workload c4'
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; bench._start_watchdog(0.3, 0); time.sleep(30)") % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 124 and 'watchdog' in out.stdout
