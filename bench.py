@@ -1070,7 +1070,7 @@ def main():
     ap.add_argument('--no-iteration', action='store_true', help='skip the MLP+loss+Adam full-iteration section')
     ap.add_argument('--no-workloads', action='store_true', help='skip the ns / c3 / c4 / c5 section')
     ap.add_argument('--headline-only', action='store_true', help='only value / e2e / kernels (quick runs)')
-    ap.add_argument('--watchdog', type=float, default=600.0,
+    ap.add_argument('--watchdog', type=float, default=360.0,
                     help='seconds after which a run that has not finished prints what it has and exits (0: off)')
     ap.add_argument('--allreduce', default='multimem', choices=['multimem', 'nccl'],
                     help='gradient exchange for N > 1: in-switch multimem kernel over symmetric memory, or NCCL')
