@@ -234,7 +234,7 @@ def sp_warp(points: Tensor, sp_points: Tensor, sp_t: Tensor, sp_r: Tensor, sp_ro
 
     lietorch (un-vendored, "parity unpinned" for its internals) supplies SE3.act(p) = R(q) p + t (lie.h:246, q used as
     is) and returns gradients w.r.t. the 7-vector projected onto the tangent space at (t, q) (FromVec backward: tangent
-    gradient times pinv of the orthogonal projector).  Both are reproduced by evaluating the action with q / |q|: equal
+    gradient times pinv of the orthogonal projector, whose in-tree copy is my_ext/_C/include/lie.h:82-90,303-311).  Both are reproduced by evaluating the action with q / |q|: equal
     values for the unit quaternions `sp_stage` passes (:847), and autograd through the normalisation IS that projection.
     Pinned on the reference's own `warp` code run with a functional lietorch stand-in: tests/golden/sp_stage.npz."""
     q = q_normalize(sp_r)

@@ -27,6 +27,43 @@ def _skeleton(joints, sk_r, sk_d_rot, sk_d_scale, g_tr, parents, root, K, mode, 
     return sk
 
 
+def global_transform(g_tr: Optional[Tensor]) -> Optional[Tensor]:
+    """The global transform in the 7-vector form (t, q xyzw) the kernels take, from any of the forms `kinematic`
+    accepts (/root/reference/networks/sk_gs.py:1092-1103): None, a 7-vector, a 6-vector twist (tau, phi) mapped by the
+    SE3 exponential (lietorch SE3::Exp = (SO3::Exp(phi), V(phi) tau) with the left Jacobian V,
+    my_ext/_C/include/lie.h:323-331,161-176,142-159) or a [4, 4] matrix (ops_3d.rigid.Rt_to_quaternion,
+    my_ext/ops_3d/rigid.py:196-205).  A handful of torch operations on seven numbers, differentiable; lietorch `SE3`
+    objects are not accepted (pass `.vec()`)."""
+    if g_tr is None:
+        return None
+    if g_tr.shape[-2:] == (4, 4):
+        Rt = g_tr.reshape(4, 4)
+        w = 0.5 * torch.sqrt((Rt[0, 0] + Rt[1, 1] + Rt[2, 2] + 1).clamp_min(1e-10))
+        w_ = 0.25 / w
+        q = torch.stack([(Rt[2, 1] - Rt[1, 2]) * w_, (Rt[0, 2] - Rt[2, 0]) * w_, (Rt[1, 0] - Rt[0, 1]) * w_, w])
+        return torch.cat([Rt[:3, 3], torch.nn.functional.normalize(q, dim=-1)])
+    v = g_tr.reshape(-1)
+    if v.numel() == 7:
+        return v
+    if v.numel() != 6:
+        raise ValueError(f'g_tr got shape {tuple(g_tr.shape)}')  # same message as sk_gs.py:1103
+    tau, phi = v[:3], v[3:]
+    theta2 = (phi * phi).sum()
+    theta = torch.sqrt(theta2)
+    small = bool(theta < 1e-6)  # lie.h EPS: Taylor branches
+    if small:
+        imag, real = 0.5 - theta2 / 48.0 + theta2 * theta2 / 3840.0, 1.0 - theta2 / 8.0 + theta2 * theta2 / 384.0
+        c1, c2 = 0.5 - theta2 / 24.0, 1.0 / 6.0 - theta2 / 120.0
+    else:
+        imag, real = torch.sin(0.5 * theta) / theta, torch.cos(0.5 * theta)
+        c1, c2 = (1.0 - torch.cos(theta)) / theta2, (theta - torch.sin(theta)) / (theta2 * theta)
+    q = torch.nn.functional.normalize(torch.cat([imag * phi, real.reshape(1) if torch.is_tensor(real) else
+                                                 phi.new_tensor([real])]), dim=-1)
+    pt = torch.linalg.cross(phi, tau)
+    t = tau + c1 * pt + c2 * torch.linalg.cross(phi, pt)  # (I + c1 [phi]x + c2 [phi]x^2) tau
+    return torch.cat([t, q])
+
+
 class _FkLbs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, root, K,
@@ -120,6 +157,7 @@ def fk_lbs(xyz: Tensor, joints: Tensor, sk_r: Tensor, sk_d_rot: Tensor, sk_d_sca
            sk_r_delta: Optional[Tensor] = None):
     """Returns the 9-tuple of `sk_stage` (networks/sk_gs.py:1150):
     (d_xyz[P,3], d_rot[P,4], d_scale[P,3], sk_T[M,7], sk_d_rot[M,4], sk_d_scale[M,3], g_tr[7], weights[P,K], indices[P,K])."""
+    g_tr = global_transform(g_tr)  # 6-vector twist / 4x4 matrix -> (t, q), as `kinematic` does (:1092-1103)
     d_xyz, d_rot, d_scale, sk_T, weights, indices = _FkLbs.apply(
         xyz, joints, sk_r, sk_d_rot, sk_d_scale, g_tr, sp_W, sp_radius, sp_weight, parents, root, K, mode, temperature,
         sk_r_delta)

@@ -124,3 +124,37 @@ def test_adam_is_a_torch_optimizer():
     opt.step()  # still no gradient: no library call on CPU tensors
     with pytest.raises(ValueError):
         Adam([a], lr=-1.0)
+
+
+def test_global_transform_forms_of_kinematic():
+    """g_tr as 7-vector, 6-vector twist (SE3 exponential) and 4x4 matrix (networks/sk_gs.py:1092-1103): the twist form
+    against the matrix exponential of the 4x4 twist matrix, the matrix form against its own rotation, both with autograd."""
+    import torch
+    from sk_gs_b200.fk_lbs import global_transform
+    from oracle import fk_lbs as OF
+    g = torch.Generator().manual_seed(3)
+    assert global_transform(None) is None
+    v7 = torch.randn(7, generator=g).double()
+    assert torch.equal(global_transform(v7), v7)
+    for scale in (1.0, 1e-9):
+        xi = (torch.randn(6, generator=g).double() * scale).requires_grad_()
+        T7 = global_transform(xi)
+        tau, phi = xi[:3].detach(), xi[3:].detach()
+        hat = torch.tensor([[0, -phi[2], phi[1]], [phi[2], 0, -phi[0]], [-phi[1], phi[0], 0]], dtype=torch.float64)
+        A = torch.zeros(4, 4, dtype=torch.float64)
+        A[:3, :3], A[:3, 3] = hat, tau
+        E = torch.linalg.matrix_exp(A)
+        assert (T7[:3].detach() - E[:3, 3]).abs().max() <= 1e-12
+        p = torch.randn(5, 3, generator=g).double()
+        assert (OF.q_rotate(T7[3:].detach(), p) - p @ E[:3, :3].T).abs().max() <= 1e-12
+        T7.sum().backward()
+        assert torch.isfinite(xi.grad).all()
+        # the matrix form of the same transform gives the same 7-vector (up to the sign of q)
+        back = global_transform(E)
+        sign = torch.sign((back[3:] * T7[3:].detach()).sum())
+        assert (back[:3] - T7[:3].detach()).abs().max() <= 1e-12 and (sign * back[3:] - T7[3:].detach()).abs().max() <= 1e-9
+    try:
+        global_transform(torch.zeros(5))
+        assert False
+    except ValueError as e:
+        assert 'g_tr got shape' in str(e)
